@@ -1,0 +1,111 @@
+// Shared helpers for libdfw_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dfw_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdfw_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace dfw {
+
+void set_error(const char* fmt, ...);
+
+#define DFW_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            dfw::set_error(__VA_ARGS__);  \
+            return 1;                     \
+        }                                 \
+    } while (0)
+
+#define DFW_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            dfw::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                       \
+            return 2;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+#define DFW_LAUNCH_CHECK() DFW_CUDA(cudaGetLastError())
+
+constexpr int kNumSMs = 148;  // B200
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- dtype helpers ---------------------------------------------------------------------
+template <typename T>
+struct Vec16;  // 16-byte vector of T
+template <>
+struct Vec16<float> {
+    static constexpr int N = 4;
+    float4 v;
+    __device__ __forceinline__ void to_float(float* f) const {
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+    __device__ __forceinline__ void from_float(const float* f) { v = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    uint4 v;
+    __device__ __forceinline__ void to_float(float* f) const {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ __forceinline__ void from_float(const float* f) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&p);
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float x);
+template <>
+__device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// Counter-based dropout RNG: keep-mask is a pure function of (seed, element index), so the
+// backward regenerates it instead of storing a mask.  splitmix64 finaliser.
+__device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return static_cast<uint32_t>(z >> 32);
+}
+// keep iff bits >= threshold, threshold = p * 2^32
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+    double t = static_cast<double>(p) * 4294967296.0;
+    if (t < 0) t = 0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    return static_cast<uint32_t>(t);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace dfw

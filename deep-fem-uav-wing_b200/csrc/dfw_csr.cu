@@ -1,0 +1,306 @@
+// (a) edge_index -> canonical CSR, built on the device.
+//
+// Replaces the per-call gather / scatter bookkeeping that PyG's SAGEConv performs on the raw
+// COO edge list (reference call site: src/deep_fem_uav_wing/gnn/model.py:90; edge_index int64
+// [2,E] in arbitrary order, gnn/dataset.py:39-63).  Result is bit-identical to
+// numpy.lexsort((src, dst)) whatever the input order:
+//     count (int atomics: order-independent) -> scan -> bucket fill (order inside a row is
+//     arbitrary here) -> per-row sort of the 64-bit key (col << 32 | edge id) (canonical).
+// HBM-bound integer work: every pass is a coalesced grid-stride sweep; the grid is a multiple
+// of the SM count.
+#include "dfw_common.cuh"
+
+namespace dfw {
+namespace {
+
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+constexpr int kBigRowSmemKeys = 4096;
+constexpr int kWarpRowMax = 32;
+
+struct CsrWs {
+    uint64_t* keys;
+    int32_t* cursor;
+    int32_t* worklist;
+    int32_t* blocksums;
+    int32_t* counters;
+    size_t bytes;
+};
+
+CsrWs carve(void* ws, int64_t E, int64_t N) {
+    CsrWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += align_up(bytes, 256);
+        return o;
+    };
+    size_t o_keys = take(sizeof(uint64_t) * (size_t)(E > 0 ? E : 1));
+    size_t o_cursor = take(sizeof(int32_t) * (size_t)(N + 1));
+    size_t o_work = take(sizeof(int32_t) * (size_t)(E / (kWarpRowMax + 1) + 1));
+    size_t nblk = (size_t)((N + 1 + kScanChunk - 1) / kScanChunk);
+    size_t o_bs = take(sizeof(int32_t) * (nblk + 1));
+    size_t o_cnt = take(sizeof(int32_t) * 4);
+    char* base = reinterpret_cast<char*>(ws);
+    w.keys = reinterpret_cast<uint64_t*>(base + o_keys);
+    w.cursor = reinterpret_cast<int32_t*>(base + o_cursor);
+    w.worklist = reinterpret_cast<int32_t*>(base + o_work);
+    w.blocksums = reinterpret_cast<int32_t*>(base + o_bs);
+    w.counters = reinterpret_cast<int32_t*>(base + o_cnt);
+    w.bytes = off;
+    return w;
+}
+
+__global__ void k_count(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t E,
+                        int64_t N, int32_t* __restrict__ cnt_plus1, int32_t* __restrict__ status) {
+    int bad = 0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = rows[e], c = cols[e];
+        if ((uint64_t)r >= (uint64_t)N || (uint64_t)c >= (uint64_t)N) {
+            ++bad;
+        } else {
+            atomicAdd(&cnt_plus1[r + 1], 1);
+        }
+    }
+    if (bad) atomicAdd(&status[0], bad);
+}
+
+// ---- 3-phase inclusive scan over a[0..n) (int32) ----------------------------------------
+__device__ __forceinline__ int block_inclusive_scan(int v, int* smem /*32 ints*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) smem[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int s = smem[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        smem[lane] = s;
+    }
+    __syncthreads();
+    if (wid > 0) v += smem[wid - 1];
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_partial(const int32_t* __restrict__ a, int64_t n,
+                                                                int32_t* __restrict__ blocksums) {
+    __shared__ int sm[32];
+    int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+        if (base + i < n) s += a[base + i];
+    int incl = block_inclusive_scan(s, sm);
+    if (threadIdx.x == kScanThreads - 1) blocksums[blockIdx.x] = incl;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_blocksums(int32_t* __restrict__ blocksums, int nblk) {
+    __shared__ int sm[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nblk; base += kScanThreads) {
+        int i = base + threadIdx.x;
+        int v = i < nblk ? blocksums[i] : 0;
+        int incl = block_inclusive_scan(v, sm);
+        int carry = carry_s;
+        if (i < nblk) blocksums[i] = carry + incl - v;  // exclusive
+        __syncthreads();
+        if (threadIdx.x == kScanThreads - 1) carry_s = carry + incl;
+        __syncthreads();
+    }
+}
+
+// a = [0, deg_0, deg_1, ...] (length N+1) -> inclusive scan in place == rowptr.  Also emits
+// cursor[i] = rowptr[i], inv_deg[i] = 1/max(deg_i,1), max degree.
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(int32_t* __restrict__ a, int64_t n /*N+1*/,
+                                                              const int32_t* __restrict__ blocksums,
+                                                              int32_t* __restrict__ cursor, float* __restrict__ inv_deg,
+                                                              int32_t* __restrict__ status) {
+    __shared__ int sm[32];
+    int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0, mx = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        v[i] = (base + i < n) ? a[base + i] : 0;
+        s += v[i];
+        mx = max(mx, v[i]);
+    }
+    int incl = block_inclusive_scan(s, sm);
+    int run = blocksums[blockIdx.x] + incl - s;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        int64_t j = base + i;
+        run += v[i];
+        if (j < n) {
+            a[j] = run;
+            if (j < n - 1) cursor[j] = run;
+            if (j >= 1 && inv_deg) inv_deg[j - 1] = 1.0f / (float)max(v[i], 1);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&status[1], mx);
+}
+
+__global__ void k_fill(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t E, int64_t N,
+                       int32_t* __restrict__ cursor, uint64_t* __restrict__ keys) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = rows[e], c = cols[e];
+        if ((uint64_t)r < (uint64_t)N && (uint64_t)c < (uint64_t)N) {
+            int pos = atomicAdd(&cursor[r], 1);
+            keys[pos] = ((uint64_t)c << 32) | (uint64_t)(uint32_t)e;
+        }
+    }
+}
+
+// one warp per row, rank sort for deg <= 32 (keys are unique: the edge id is part of the key)
+__global__ void __launch_bounds__(256) k_sort_rows_warp(const int32_t* __restrict__ rowptr, int64_t N,
+                                                         const uint64_t* __restrict__ keys, int32_t* __restrict__ col,
+                                                         int32_t* __restrict__ perm, int32_t* __restrict__ worklist,
+                                                         int32_t* __restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += warps) {
+        const int beg = rowptr[row], deg = rowptr[row + 1] - beg;
+        if (deg == 0) continue;
+        if (deg > kWarpRowMax) {
+            if (lane == 0) worklist[atomicAdd(&counters[0], 1)] = (int32_t)row;
+            continue;
+        }
+        uint64_t k = lane < deg ? keys[beg + lane] : ~0ull;
+        int rank = 0;
+        for (int j = 0; j < deg; ++j) {
+            uint64_t o = __shfl_sync(0xffffffffu, k, j);
+            rank += (o < k);
+        }
+        if (lane < deg) {
+            col[beg + rank] = (int32_t)(k >> 32);
+            if (perm) perm[beg + rank] = (int32_t)(k & 0xffffffffu);
+        }
+    }
+}
+
+// ascending-only bitonic network (first step of every merge mirrors, the rest butterfly), so
+// virtual +inf padding above `n` never moves: pairs whose upper index is >= n are skipped.
+template <typename Ptr>
+__device__ __forceinline__ void bitonic_ascending(Ptr a, int n) {
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {  // mirror step
+            int blk = t / (k / 2), off = t % (k / 2);
+            int lo = blk * k + off, hi = blk * k + (k - 1 - off);
+            if (hi < n) {
+                uint64_t x = a[lo], y = a[hi];
+                if (y < x) { a[lo] = y; a[hi] = x; }
+            }
+        }
+        __syncthreads();
+        for (int j = k / 4; j >= 1; j >>= 1) {
+            for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                int lo = (t / j) * (2 * j) + (t % j), hi = lo + j;
+                if (hi < n) {
+                    uint64_t x = a[lo], y = a[hi];
+                    if (y < x) { a[lo] = y; a[hi] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sort_rows_big(const int32_t* __restrict__ rowptr, uint64_t* __restrict__ keys,
+                                                        int32_t* __restrict__ col, int32_t* __restrict__ perm,
+                                                        const int32_t* __restrict__ worklist,
+                                                        const int32_t* __restrict__ counters) {
+    __shared__ uint64_t sk[kBigRowSmemKeys];
+    const int nwork = counters[0];
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int row = worklist[w];
+        const int beg = rowptr[row], deg = rowptr[row + 1] - beg;
+        if (deg <= kBigRowSmemKeys) {
+            for (int i = threadIdx.x; i < deg; i += blockDim.x) sk[i] = keys[beg + i];
+            __syncthreads();
+            bitonic_ascending(sk, deg);
+            for (int i = threadIdx.x; i < deg; i += blockDim.x) {
+                uint64_t k = sk[i];
+                col[beg + i] = (int32_t)(k >> 32);
+                if (perm) perm[beg + i] = (int32_t)(k & 0xffffffffu);
+            }
+            __syncthreads();
+        } else {
+            bitonic_ascending(keys + beg, deg);  // in global memory; block-level syncs order the passes
+            for (int i = threadIdx.x; i < deg; i += blockDim.x) {
+                uint64_t k = keys[beg + i];
+                col[beg + i] = (int32_t)(k >> 32);
+                if (perm) perm[beg + i] = (int32_t)(k & 0xffffffffu);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace
+}  // namespace dfw
+
+extern "C" size_t dfw_csr_ws_bytes(int64_t E, int64_t N) {
+    if (E < 0 || N < 0) return 0;
+    return dfw::carve(nullptr, E, N).bytes;
+}
+
+extern "C" int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src, int32_t* rowptr,
+                             int32_t* col, int32_t* perm, float* inv_deg, int32_t* status, void* ws,
+                             size_t ws_bytes, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(E >= 0 && N >= 0, "dfw_csr_build: negative size (E=%lld, N=%lld)", (long long)E, (long long)N);
+    DFW_REQUIRE(E < 2147483647LL && N < 2147483647LL, "dfw_csr_build: E and N must be < 2^31 (E=%lld, N=%lld)",
+                (long long)E, (long long)N);
+    DFW_REQUIRE(rowptr && status && (col || E == 0), "dfw_csr_build: null output pointer");
+    DFW_REQUIRE(edge_index || E == 0, "dfw_csr_build: null edge_index");
+    CsrWs w = carve(ws, E, N);
+    DFW_REQUIRE(ws && ws_bytes >= w.bytes, "dfw_csr_build: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+
+    DFW_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * (size_t)(N + 1), s));
+    DFW_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * 2, s));
+    DFW_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int32_t) * 4, s));
+
+    const int64_t* rows = by_src ? edge_index : edge_index + E;
+    const int64_t* cols = by_src ? edge_index + E : edge_index;
+    const int threads = 256;
+    const int grid_e = (int)std::max<int64_t>(1, std::min<int64_t>((E + threads - 1) / threads, (int64_t)kNumSMs * 16));
+    if (E > 0) {
+        k_count<<<grid_e, threads, 0, s>>>(rows, cols, E, N, rowptr, status);
+        DFW_LAUNCH_CHECK();
+    }
+    const int64_t n1 = N + 1;
+    const int nblk = (int)((n1 + kScanChunk - 1) / kScanChunk);
+    k_scan_partial<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, w.blocksums);
+    DFW_LAUNCH_CHECK();
+    k_scan_blocksums<<<1, kScanThreads, 0, s>>>(w.blocksums, nblk);
+    DFW_LAUNCH_CHECK();
+    k_scan_apply<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, w.blocksums, w.cursor, inv_deg, status);
+    DFW_LAUNCH_CHECK();
+    if (E > 0) {
+        k_fill<<<grid_e, threads, 0, s>>>(rows, cols, E, N, w.cursor, w.keys);
+        DFW_LAUNCH_CHECK();
+        const int64_t warps_per_block = threads / 32;
+        const int grid_r = (int)std::max<int64_t>(1, std::min<int64_t>((N + warps_per_block - 1) / warps_per_block, (int64_t)kNumSMs * 64));
+        k_sort_rows_warp<<<grid_r, threads, 0, s>>>(rowptr, N, w.keys, col, perm, w.worklist, w.counters);
+        DFW_LAUNCH_CHECK();
+        k_sort_rows_big<<<kNumSMs * 2, 256, 0, s>>>(rowptr, w.keys, col, perm, w.worklist, w.counters);
+        DFW_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -1,0 +1,605 @@
+// (c)/(d) node-wise dense contractions of the GraphSAGE layer, SIMT-FP32 edition.
+//
+//   fwd : y = a1.w1^T (+ a2.w2^T) + bias ; out = residual + dropout(relu(layernorm(y)))
+//         = SAGEConv's lin_l(mean) + lin_r(h) (PyG; reference call site model.py:90) with the
+//           LayerNorm / ReLU / dropout / skip of model.py:91-95 fused into the epilogue, and the
+//           encoder / decoder linears of model.py:52-57,67-72.
+//   dx  : g_a = row_scale * (g_y . w) + addend
+//   dw  : dW = g_y^T . a  (split over nodes, fixed-order second pass: no float atomics)
+//
+// One register-tiled kernel template serves the three contractions; only the tile loaders and
+// the epilogue differ.  A CTA tile always spans the full output row (Hout <= 256), so the
+// LayerNorm statistics are reduced inside the CTA with shuffles.  This is the exact-fp32
+// path (FFMA); the tensor-core path lives in dfw_linear_tc.cu.
+#include <algorithm>
+#include <type_traits>
+
+#include "dfw_common.cuh"
+
+namespace dfw {
+namespace {
+
+constexpr int BK = 16;
+constexpr int PAD = 4;
+constexpr int kThreads = 256;
+
+enum Mode { MODE_FWD = 0, MODE_DX = 1, MODE_DW = 2 };
+
+struct LinArgs {
+    // operands (meaning depends on mode)
+    const void* a1; const void* w1; int64_t k1;
+    const void* a2; const void* w2; int64_t k2;
+    const float* bias; const float* gamma; const float* beta; float eps;
+    const void* residual; float dropout_p; uint32_t drop_thr; float drop_scale; uint64_t seed;
+    void* out; void* pre_out; float* ln_stats;
+    const float* rowdot_w; const float* rowdot_b; float* rowdot_out;
+    const float* row_scale; const void* addend;
+    int64_t N; int64_t Hout; int64_t K; int flags;
+    // dW
+    float* part; float* part_db; int splits; int64_t nodes_per_split; int tiles_i; int tiles_j1; int tiles_j2;
+};
+
+// ---- tile loaders --------------------------------------------------------------------------
+// "Transposed" source: S[kk][idx] = M[idx_base+idx][k_base+kk]   (M row-major, leading dim ld)
+template <typename T, int TILE>
+struct TLoad {
+    static constexpr int VE = 16 / sizeof(T);
+    static constexpr int CH = BK / VE;
+    static constexpr int ITEMS = TILE * CH;
+    static constexpr int PER = (ITEMS + kThreads - 1) / kThreads;
+    float r[PER][VE];
+    __device__ __forceinline__ void load(const T* __restrict__ M, int64_t ld, int64_t idx_base, int64_t idx_lim,
+                                         int64_t k_base, int64_t k_lim, bool vec_ok) {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int item = threadIdx.x + p * kThreads;
+            if (ITEMS % kThreads != 0 && item >= ITEMS) break;
+            const int row = item / CH, ch = item % CH;
+            const int64_t gi = idx_base + row, gk = k_base + ch * VE;
+            if (gi < idx_lim && vec_ok && gk + VE <= k_lim) {
+                Vec16<T> v;
+                v.v = *reinterpret_cast<const decltype(v.v)*>(M + gi * ld + gk);
+                v.to_float(r[p]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VE; ++e)
+                    r[p][e] = (gi < idx_lim && gk + e < k_lim) ? to_f32(M[gi * ld + gk + e]) : 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(float* __restrict__ S) const {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int item = threadIdx.x + p * kThreads;
+            if (ITEMS % kThreads != 0 && item >= ITEMS) break;
+            const int row = item / CH, ch = item % CH;
+#pragma unroll
+            for (int e = 0; e < VE; ++e) S[(ch * VE + e) * (TILE + PAD) + row] = r[p][e];
+        }
+    }
+};
+
+// "Direct" source: S[kk][idx] = M[k_base+kk][idx_base+idx]
+template <typename T, int TILE>
+struct DLoad {
+    static constexpr int VE = 16 / sizeof(T);
+    static constexpr int CH = TILE / VE;
+    static constexpr int ITEMS = BK * CH;
+    static constexpr int PER = (ITEMS + kThreads - 1) / kThreads;
+    float r[PER][VE];
+    __device__ __forceinline__ void load(const T* __restrict__ M, int64_t ld, int64_t idx_base, int64_t idx_lim,
+                                         int64_t k_base, int64_t k_lim, bool vec_ok) {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int item = threadIdx.x + p * kThreads;
+            if (ITEMS % kThreads != 0 && item >= ITEMS) break;
+            const int kk = item / CH, ch = item % CH;
+            const int64_t gk = k_base + kk, gi = idx_base + ch * VE;
+            if (gk < k_lim && vec_ok && gi + VE <= idx_lim) {
+                Vec16<T> v;
+                v.v = *reinterpret_cast<const decltype(v.v)*>(M + gk * ld + gi);
+                v.to_float(r[p]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VE; ++e)
+                    r[p][e] = (gk < k_lim && gi + e < idx_lim) ? to_f32(M[gk * ld + gi + e]) : 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(float* __restrict__ S) const {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int item = threadIdx.x + p * kThreads;
+            if (ITEMS % kThreads != 0 && item >= ITEMS) break;
+            const int kk = item / CH, ch = item % CH;
+            float* d = S + kk * (TILE + PAD) + ch * VE;
+#pragma unroll
+            for (int e = 0; e < VE; e += 4) *reinterpret_cast<float4*>(d + e) = make_float4(r[p][e], r[p][e + 1], r[p][e + 2], r[p][e + 3]);
+        }
+    }
+};
+
+template <int T_, int HALF>
+__device__ __forceinline__ int tile_index(int t, int i) {
+    // thread t owns T_ indices: [t*4, t*4+4) and, if T_==8, [HALF + t*4, HALF + t*4 + 4)
+    return (i < 4) ? t * 4 + i : HALF + t * 4 + (i - 4);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_row4(T* __restrict__ base, int64_t row, int64_t ld, int c0, int64_t clim,
+                                           const float* v, bool vec_ok) {
+    if (vec_ok && c0 + 4 <= clim) {
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(base + row * ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+            *reinterpret_cast<uint2*>(base + row * ld + c0) = u;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (c0 + j < clim) base[row * ld + c0 + j] = from_f32<T>(v[j]);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void load_row4(const T* __restrict__ base, int64_t row, int64_t ld, int c0, int64_t clim,
+                                          float* v, bool vec_ok) {
+    if (vec_ok && c0 + 4 <= clim) {
+        if constexpr (sizeof(T) == 4) {
+            float4 f = *reinterpret_cast<const float4*>(base + row * ld + c0);
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+            uint2 u = *reinterpret_cast<const uint2*>(base + row * ld + c0);
+            v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+            v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (c0 + j < clim) ? to_f32(base[row * ld + c0 + j]) : 0.f;
+    }
+}
+
+template <int TX>
+__device__ __forceinline__ float row_group_sum(float v) {
+#pragma unroll
+    for (int o = TX / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- the kernel ----------------------------------------------------------------------------
+template <typename T, int MODE, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(kThreads) k_linear(const LinArgs p) {
+    constexpr int TX = BN / TN, TY = BM / TM;
+    static_assert(TX * TY == kThreads, "thread layout");
+    static_assert(TX == 16 || TX == 32, "row reduction width");
+    extern __shared__ __align__(16) float smem[];
+    constexpr int A_STAGE = BK * (BM + PAD), B_STAGE = BK * (BN + PAD);
+    float* const As0 = smem;
+    float* const Bs0 = smem + 2 * A_STAGE;
+
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    // ---- problem mapping ------------------------------------------------------------------
+    // FWD: rows = nodes (M), cols = Hout, reduce over k1 then k2.   A: TLoad(a), B: TLoad(w)
+    // DX : rows = nodes (M), cols = K (tile blockIdx.y), reduce over Hout.  A: TLoad(g_y), B: DLoad(w)
+    // DW : rows = Hout (tile i), cols = K of a1 or a2 (tile j), reduce over a node range.
+    //      A: DLoad(g_y), B: DLoad(a)
+    int64_t m_base = 0, n_base = 0;
+    int seg_count = 1;
+    int tile_i = 0, tile_j = 0, split = 0, which = 0;
+    int64_t red_begin = 0, red_end = 0;
+    if (MODE == MODE_FWD) {
+        m_base = (int64_t)blockIdx.x * BM;
+        seg_count = p.a2 ? 2 : 1;
+    } else if (MODE == MODE_DX) {
+        m_base = (int64_t)blockIdx.x * BM;
+        n_base = (int64_t)blockIdx.y * BN;
+    } else {
+        const int tiles_j = p.tiles_j1 + p.tiles_j2;
+        const int tile = blockIdx.x;
+        tile_i = tile / tiles_j;
+        tile_j = tile % tiles_j;
+        which = tile_j >= p.tiles_j1;
+        if (which) tile_j -= p.tiles_j1;
+        split = blockIdx.y;
+        m_base = (int64_t)tile_i * BM;
+        n_base = (int64_t)tile_j * BN;
+        red_begin = (int64_t)split * p.nodes_per_split;
+        red_end = min(p.N, red_begin + p.nodes_per_split);
+    }
+
+    float db_acc = 0.f;  // MODE_DW: column sum of g_y handled by thread (threadIdx.x < BM)
+
+    for (int seg = 0; seg < seg_count; ++seg) {
+        const T* Aop;
+        const T* Bop;
+        int64_t lda, ldb, a_idx_lim, b_idx_lim, k_begin, k_end;
+        if (MODE == MODE_FWD) {
+            Aop = (const T*)(seg == 0 ? p.a1 : p.a2);
+            Bop = (const T*)(seg == 0 ? p.w1 : p.w2);
+            const int64_t k = seg == 0 ? p.k1 : p.k2;
+            lda = k; ldb = k; a_idx_lim = p.N; b_idx_lim = p.Hout; k_begin = 0; k_end = k;
+        } else if (MODE == MODE_DX) {
+            Aop = (const T*)p.a1;  // g_y [N,Hout]
+            Bop = (const T*)p.w1;  // w [Hout,K]
+            lda = p.Hout; ldb = p.K; a_idx_lim = p.N; b_idx_lim = p.K; k_begin = 0; k_end = p.Hout;
+        } else {
+            Aop = (const T*)p.a1;                      // g_y [N,Hout]
+            Bop = (const T*)(which ? p.w2 : p.w1);     // a1 / a2 [N,k]
+            lda = p.Hout; ldb = which ? p.k2 : p.k1; a_idx_lim = p.Hout; b_idx_lim = ldb;
+            k_begin = red_begin; k_end = red_end;
+        }
+        const bool a_vec = (lda * sizeof(T)) % 16 == 0 && aligned16_dev(Aop);
+        const bool b_vec = (ldb * sizeof(T)) % 16 == 0 && aligned16_dev(Bop);
+        const int nsteps = (int)((k_end - k_begin + BK - 1) / BK);
+        if (nsteps <= 0) continue;
+
+        typename std::conditional<MODE == MODE_DW, DLoad<T, BM>, TLoad<T, BM>>::type la;
+        typename std::conditional<MODE == MODE_FWD, TLoad<T, BN>, DLoad<T, BN>>::type lb;
+
+        la.load(Aop, lda, m_base, a_idx_lim, k_begin, k_end, a_vec);
+        lb.load(Bop, ldb, n_base, b_idx_lim, k_begin, k_end, b_vec);
+        __syncthreads();  // previous segment's readers are done with buffer 0
+        la.store(As0);
+        lb.store(Bs0);
+        __syncthreads();
+
+        for (int t = 0; t < nsteps; ++t) {
+            const int cur = t & 1;
+            if (t + 1 < nsteps) {
+                la.load(Aop, lda, m_base, a_idx_lim, k_begin + (int64_t)(t + 1) * BK, k_end, a_vec);
+                lb.load(Bop, ldb, n_base, b_idx_lim, k_begin + (int64_t)(t + 1) * BK, k_end, b_vec);
+            }
+            const float* as = As0 + cur * A_STAGE;
+            const float* bs = Bs0 + cur * B_STAGE;
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                float a[TM], b[TN];
+                *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(as + kk * (BM + PAD) + ty * 4);
+                if (TM == 8) *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(as + kk * (BM + PAD) + BM / 2 + ty * 4);
+                *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(bs + kk * (BN + PAD) + tx * 4);
+                if (TN == 8) *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(bs + kk * (BN + PAD) + BN / 2 + tx * 4);
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            if (MODE == MODE_DW && p.part_db && tile_j == 0 && which == 0 && threadIdx.x < BM) {
+#pragma unroll
+                for (int kk = 0; kk < BK; ++kk) db_acc += as[kk * (BM + PAD) + threadIdx.x];
+            }
+            if (t + 1 < nsteps) {
+                la.store(As0 + (cur ^ 1) * A_STAGE);
+                lb.store(Bs0 + (cur ^ 1) * B_STAGE);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogues ------------------------------------------------------------------------
+    if (MODE == MODE_DW) {
+        const int tiles = p.tiles_i * (p.tiles_j1 + p.tiles_j2);
+        float* dst = p.part + ((int64_t)split * tiles + blockIdx.x) * (BM * BN);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int r = tile_index<TM, BM / 2>(ty, i);
+#pragma unroll
+            for (int jh = 0; jh < TN / 4; ++jh) {
+                const int c = jh == 0 ? tx * 4 : BN / 2 + tx * 4;
+                *reinterpret_cast<float4*>(dst + r * BN + c) =
+                    make_float4(acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+            }
+        }
+        if (p.part_db && tile_j == 0 && which == 0 && threadIdx.x < BM)
+            p.part_db[((int64_t)split * p.tiles_i + tile_i) * BM + threadIdx.x] = db_acc;
+        return;
+    }
+
+    const int64_t ncols = MODE == MODE_FWD ? p.Hout : p.K;
+    const bool out_vec = ncols % 4 == 0;  // 16-byte (fp32) / 8-byte (bf16) aligned 4-element groups
+
+    if (MODE == MODE_DX) {
+        T* out = (T*)p.out;
+        const T* addend = (const T*)p.addend;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int64_t r = m_base + tile_index<TM, BM / 2>(ty, i);
+            if (r >= p.N) continue;
+            const float sc = p.row_scale ? __ldg(p.row_scale + r) : 1.f;
+#pragma unroll
+            for (int jh = 0; jh < TN / 4; ++jh) {
+                const int c = (int)n_base + (jh == 0 ? tx * 4 : BN / 2 + tx * 4);
+                if (c >= ncols) continue;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = acc[i][jh * 4 + j] * sc;
+                if (addend) {
+                    float ad[4];
+                    load_row4(addend, r, ncols, c, ncols, ad, out_vec);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] += ad[j];
+                }
+                store_row4(out, r, ncols, c, ncols, v, out_vec);
+            }
+        }
+        return;
+    }
+
+    // MODE_FWD
+    {
+        const int64_t H = p.Hout;
+        const float invH = 1.f / (float)H;
+        T* out = (T*)p.out;
+        T* pre = (T*)p.pre_out;
+        const T* res = (const T*)p.residual;
+        // per-thread column constants
+        float bias[TN], gam[TN], bet[TN], rdw[TN];
+        bool cok[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int c = tile_index<TN, BN / 2>(tx, j);
+            cok[j] = c < H;
+            bias[j] = (p.bias && cok[j]) ? __ldg(p.bias + c) : 0.f;
+            gam[j] = (p.gamma && cok[j]) ? __ldg(p.gamma + c) : 1.f;
+            bet[j] = (p.beta && cok[j]) ? __ldg(p.beta + c) : 0.f;
+            rdw[j] = (p.rowdot_w && cok[j]) ? __ldg(p.rowdot_w + c) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int64_t r = m_base + tile_index<TM, BM / 2>(ty, i);
+            const bool rok = r < p.N;  // no early exit: shuffles below need the whole row group
+            float v[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) v[j] = cok[j] ? acc[i][j] + bias[j] : 0.f;
+            if (pre && rok) {
+#pragma unroll
+                for (int jh = 0; jh < TN / 4; ++jh) {
+                    const int c = jh == 0 ? tx * 4 : BN / 2 + tx * 4;
+                    if (c < H) store_row4(pre, r, H, c, H, v + jh * 4, out_vec);
+                }
+            }
+            if (p.flags & DFW_EP_LAYERNORM) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < TN; ++j) s += v[j];
+                const float mean = row_group_sum<TX>(s) * invH;
+                float q = 0.f;
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    const float d = cok[j] ? v[j] - mean : 0.f;
+                    q += d * d;
+                }
+                const float var = row_group_sum<TX>(q) * invH;
+                const float rstd = rsqrtf(var + p.eps);
+                if (p.ln_stats && rok && tx == 0) {
+                    p.ln_stats[2 * r] = mean;
+                    p.ln_stats[2 * r + 1] = rstd;
+                }
+#pragma unroll
+                for (int j = 0; j < TN; ++j) v[j] = (v[j] - mean) * rstd * gam[j] + bet[j];
+            }
+            if (p.flags & DFW_EP_RELU) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.flags & DFW_EP_DROPOUT) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    const int c = tile_index<TN, BN / 2>(tx, j);
+                    const uint32_t bits = dropout_bits(p.seed, (uint64_t)r * (uint64_t)H + (uint64_t)c);
+                    v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
+                }
+            }
+            if (p.rowdot_out) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < TN; ++j) s += cok[j] ? v[j] * rdw[j] : 0.f;
+                s = row_group_sum<TX>(s);
+                if (rok && tx == 0) p.rowdot_out[r] = s + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
+            }
+            if (out && rok) {
+#pragma unroll
+                for (int jh = 0; jh < TN / 4; ++jh) {
+                    const int c = jh == 0 ? tx * 4 : BN / 2 + tx * 4;
+                    if (c >= H) continue;
+                    float w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w[j] = v[jh * 4 + j];
+                    if (res) {
+                        float rr[4];
+                        load_row4(res, r, H, c, H, rr, out_vec);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) w[j] += rr[j];
+                    }
+                    store_row4(out, r, H, c, H, w, out_vec);
+                }
+            }
+        }
+    }
+}
+
+// second pass of dW: fixed-order sum over splits
+template <int BM, int BN>
+__global__ void k_dw_reduce(const float* __restrict__ part, const float* __restrict__ part_db, int splits, int tiles_i,
+                            int tiles_j1, int tiles_j2, int64_t Hout, int64_t k1, int64_t k2, float* __restrict__ dw1,
+                            float* __restrict__ dw2, float* __restrict__ dbias, int accumulate) {
+    const int64_t n1 = Hout * k1, n2 = Hout * k2;
+    const int64_t total = n1 + n2 + (dbias ? Hout : 0);
+    const int tiles = tiles_i * (tiles_j1 + tiles_j2);
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        float* dst;
+        if (idx < n1 + n2) {
+            const bool second = idx >= n1;
+            const int64_t e = second ? idx - n1 : idx;
+            const int64_t k = second ? k2 : k1;
+            const int64_t i = e / k, j = e % k;
+            const int ti = (int)(i / BM), tj = (int)(j / BN) + (second ? tiles_j1 : 0);
+            const int64_t off = (int64_t)(ti * (tiles_j1 + tiles_j2) + tj) * (BM * BN) + (i % BM) * BN + (j % BN);
+            for (int sp = 0; sp < splits; ++sp) s += part[(int64_t)sp * tiles * (BM * BN) + off];
+            dst = (second ? dw2 : dw1) + e;
+        } else {
+            const int64_t i = idx - n1 - n2;
+            const int ti = (int)(i / BM);
+            for (int sp = 0; sp < splits; ++sp) s += part_db[((int64_t)sp * tiles_i + ti) * BM + (i % BM)];
+            dst = dbias + i;
+        }
+        *dst = accumulate ? *dst + s : s;
+    }
+}
+
+template <typename T, int MODE, int BM, int BN, int TM, int TN>
+int launch_linear(const LinArgs& a, dim3 grid, cudaStream_t s) {
+    constexpr size_t smem = sizeof(float) * 2 * BK * ((BM + PAD) + (BN + PAD));
+    static_assert(smem <= 48 * 1024, "static-range shared memory");
+    k_linear<T, MODE, BM, BN, TM, TN><<<grid, kThreads, smem, s>>>(a);
+    DFW_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T, int MODE>
+int dispatch_cols(const LinArgs& a, int64_t ncols_tile, dim3 grid64, dim3 grid128, dim3 grid256, cudaStream_t s) {
+    if (ncols_tile <= 64) return launch_linear<T, MODE, 128, 64, 8, 4>(a, grid64, s);
+    if (ncols_tile <= 128) return launch_linear<T, MODE, 128, 128, 8, 8>(a, grid128, s);
+    return launch_linear<T, MODE, 64, 256, 8, 8>(a, grid256, s);
+}
+
+inline dim3 grid_rows(int64_t N, int BM, int64_t ytiles = 1) { return dim3((unsigned)((N + BM - 1) / BM), (unsigned)ytiles, 1); }
+
+}  // namespace
+}  // namespace dfw
+
+extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const void* a2, const void* w2, int64_t k2,
+                              const float* bias, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                              const void* residual, float dropout_p, uint64_t seed, void* out, void* pre_out,
+                              float* ln_stats, const float* rowdot_w, const float* rowdot_b, float* rowdot_out, int64_t N,
+                              int64_t Hout, int flags, int dtype, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_linear_fwd: unknown dtype %d", dtype);
+    DFW_REQUIRE(N >= 0 && Hout >= 1 && Hout <= 256, "dfw_linear_fwd: Hout=%lld must be in [1,256] (N=%lld)",
+                (long long)Hout, (long long)N);
+    DFW_REQUIRE(a1 && w1 && k1 >= 1, "dfw_linear_fwd: a1/w1 required");
+    DFW_REQUIRE((a2 == nullptr) == (w2 == nullptr), "dfw_linear_fwd: a2 and w2 go together");
+    DFW_REQUIRE(!a2 || k2 >= 1, "dfw_linear_fwd: k2 must be >= 1 with a2");
+    DFW_REQUIRE(out || rowdot_out, "dfw_linear_fwd: no output requested");
+    DFW_REQUIRE(!(flags & DFW_EP_RESIDUAL) || residual, "dfw_linear_fwd: DFW_EP_RESIDUAL without residual");
+    DFW_REQUIRE((rowdot_w == nullptr) == (rowdot_out == nullptr), "dfw_linear_fwd: rowdot_w and rowdot_out go together");
+    DFW_REQUIRE(!(flags & DFW_EP_DROPOUT) || (dropout_p >= 0.f && dropout_p < 1.f), "dfw_linear_fwd: dropout_p=%f not in [0,1)",
+                (double)dropout_p);
+    if (N == 0) return 0;
+    LinArgs a{};
+    a.a1 = a1; a.w1 = w1; a.k1 = k1; a.a2 = a2; a.w2 = w2; a.k2 = a2 ? k2 : 0;
+    a.bias = bias; a.gamma = ln_gamma; a.beta = ln_beta; a.eps = ln_eps;
+    a.residual = (flags & DFW_EP_RESIDUAL) ? residual : nullptr;
+    if ((flags & DFW_EP_DROPOUT) && dropout_p == 0.f) flags &= ~DFW_EP_DROPOUT;
+    a.dropout_p = dropout_p; a.drop_thr = dropout_threshold(dropout_p); a.drop_scale = 1.f / (1.f - dropout_p); a.seed = seed;
+    a.out = out; a.pre_out = pre_out; a.ln_stats = ln_stats;
+    a.rowdot_w = rowdot_w; a.rowdot_b = rowdot_b; a.rowdot_out = rowdot_out;
+    a.N = N; a.Hout = Hout; a.flags = flags;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == DFW_F32)
+        return dispatch_cols<float, MODE_FWD>(a, Hout, grid_rows(N, 128), grid_rows(N, 128), grid_rows(N, 64), s);
+    return dispatch_cols<__nv_bfloat16, MODE_FWD>(a, Hout, grid_rows(N, 128), grid_rows(N, 128), grid_rows(N, 64), s);
+}
+
+extern "C" int dfw_linear_bwd_input(const void* g_y, const void* w, const float* row_scale, const void* addend,
+                                    void* g_a, int64_t N, int64_t Hout, int64_t K, int dtype, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_linear_bwd_input: unknown dtype %d", dtype);
+    DFW_REQUIRE(N >= 0 && Hout >= 1 && K >= 1, "dfw_linear_bwd_input: bad shape");
+    DFW_REQUIRE(g_y && w && g_a, "dfw_linear_bwd_input: null pointer");
+    if (N == 0) return 0;
+    LinArgs a{};
+    a.a1 = g_y; a.w1 = w; a.row_scale = row_scale; a.addend = addend; a.out = g_a;
+    a.N = N; a.Hout = Hout; a.K = K;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t tile = K <= 64 ? 64 : (K <= 128 ? 128 : 256);
+    const int64_t yt = (K + tile - 1) / tile;
+    if (dtype == DFW_F32)
+        return dispatch_cols<float, MODE_DX>(a, tile, grid_rows(N, 128, yt), grid_rows(N, 128, yt), grid_rows(N, 64, yt), s);
+    return dispatch_cols<__nv_bfloat16, MODE_DX>(a, tile, grid_rows(N, 128, yt), grid_rows(N, 128, yt), grid_rows(N, 64, yt), s);
+}
+
+namespace dfw {
+namespace {
+struct DwPlan {
+    int tiles_i, tiles_j1, tiles_j2, splits;
+    int64_t nodes_per_split;
+    size_t part_bytes, db_bytes;
+};
+constexpr int DW_BM = 128, DW_BN = 128;
+DwPlan dw_plan(int64_t N, int64_t Hout, int64_t k1, int64_t k2) {
+    DwPlan p;
+    p.tiles_i = (int)((Hout + DW_BM - 1) / DW_BM);
+    p.tiles_j1 = (int)((k1 + DW_BN - 1) / DW_BN);
+    p.tiles_j2 = (int)((k2 + DW_BN - 1) / DW_BN);
+    const int tiles = p.tiles_i * (p.tiles_j1 + p.tiles_j2);
+    int64_t want = (2 * kNumSMs + tiles - 1) / tiles;
+    int64_t max_splits = std::max<int64_t>(1, (N + 4 * BK - 1) / (4 * BK));
+    int64_t splits = std::max<int64_t>(1, std::min(want, max_splits));
+    int64_t per = (N + splits - 1) / splits;
+    per = (per + BK - 1) / BK * BK;
+    splits = std::max<int64_t>(1, (N + per - 1) / per);
+    p.splits = (int)splits;
+    p.nodes_per_split = per;
+    p.part_bytes = align_up(sizeof(float) * (size_t)splits * tiles * DW_BM * DW_BN, 256);
+    p.db_bytes = align_up(sizeof(float) * (size_t)splits * p.tiles_i * DW_BM, 256);
+    return p;
+}
+}  // namespace
+}  // namespace dfw
+
+extern "C" size_t dfw_linear_bwd_weight_ws_bytes(int64_t N, int64_t Hout, int64_t k1, int64_t k2) {
+    if (N < 0 || Hout < 1 || k1 < 1 || k2 < 0) return 0;
+    dfw::DwPlan p = dfw::dw_plan(N, Hout, k1, k2);
+    return p.part_bytes + p.db_bytes;
+}
+
+extern "C" int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1, const void* a2, int64_t k2,
+                                     float* dw1, float* dw2, float* dbias, int64_t N, int64_t Hout, int dtype,
+                                     int accumulate, void* ws, size_t ws_bytes, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_linear_bwd_weight: unknown dtype %d", dtype);
+    DFW_REQUIRE(N >= 0 && Hout >= 1 && k1 >= 1, "dfw_linear_bwd_weight: bad shape");
+    DFW_REQUIRE(g_y && a1 && dw1, "dfw_linear_bwd_weight: null pointer");
+    DFW_REQUIRE((a2 == nullptr) == (dw2 == nullptr), "dfw_linear_bwd_weight: a2 and dw2 go together");
+    if (!a2) k2 = 0;
+    DwPlan pl = dw_plan(N, Hout, k1, k2);
+    DFW_REQUIRE(ws && ws_bytes >= pl.part_bytes + pl.db_bytes, "dfw_linear_bwd_weight: workspace too small (%zu < %zu)",
+                ws_bytes, pl.part_bytes + pl.db_bytes);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    LinArgs a{};
+    a.a1 = g_y; a.w1 = a1; a.w2 = a2; a.k1 = k1; a.k2 = k2; a.N = N; a.Hout = Hout;
+    a.part = reinterpret_cast<float*>(ws);
+    a.part_db = dbias ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes) : nullptr;
+    a.splits = pl.splits; a.nodes_per_split = pl.nodes_per_split;
+    a.tiles_i = pl.tiles_i; a.tiles_j1 = pl.tiles_j1; a.tiles_j2 = pl.tiles_j2;
+    const int tiles = pl.tiles_i * (pl.tiles_j1 + pl.tiles_j2);
+    dim3 grid((unsigned)tiles, (unsigned)pl.splits, 1);
+    int rc;
+    if (N == 0) {
+        // nothing to reduce: the second pass writes zeros (or leaves dW untouched when accumulating)
+        a.splits = 0;
+        rc = 0;
+    } else if (dtype == DFW_F32) {
+        rc = launch_linear<float, MODE_DW, DW_BM, DW_BN, 8, 8>(a, grid, s);
+    } else {
+        rc = launch_linear<__nv_bfloat16, MODE_DW, DW_BM, DW_BN, 8, 8>(a, grid, s);
+    }
+    if (rc) return rc;
+    const int64_t total = Hout * (k1 + k2) + (dbias ? Hout : 0);
+    const int rgrid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 8);
+    k_dw_reduce<DW_BM, DW_BN><<<rgrid, 256, 0, s>>>(a.part, a.part_db, a.splits, pl.tiles_i, pl.tiles_j1, pl.tiles_j2, Hout,
+                                                    k1, k2, dw1, dw2, dbias, accumulate);
+    DFW_LAUNCH_CHECK();
+    return 0;
+}

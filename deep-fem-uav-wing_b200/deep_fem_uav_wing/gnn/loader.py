@@ -1,0 +1,206 @@
+"""PyG-free ``Data`` / ``Batch`` / ``DataLoader`` with the semantics the reference relies on.
+
+The reference batches graphs with ``torch_geometric.loader.DataLoader`` (``scripts/train_gnn.py:30,150``):
+a mini-batch is the disjoint union of its graphs - node tensors concatenated, ``edge_index``
+shifted by the running node offset, plus ``batch`` (graph id per node), ``ptr`` and ``num_graphs``
+(``train_gnn.py:51-60`` uses ``.to(device)``, ``.x``, ``.edge_index``, ``.batch``, ``.y``, ``.loss_mask``,
+``.num_graphs``).  This module restates exactly that, and adds what a B200 box wants:
+
+* pinned-memory collation + asynchronous H2D on a side stream with one batch of prefetch
+  (``DataLoader(..., device=...)``), so the copy of step i+1 overlaps the compute of step i;
+* mesh-level sharding for data-parallel training (``rank`` / ``world_size`` / ``set_epoch``), the
+  ``DistributedSampler`` contract: every rank draws the same permutation and takes a strided slice.
+"""
+from __future__ import annotations
+
+from typing import Any, Iterable, Sequence
+
+import torch
+
+_NODE_KEYS_DEFAULT = ("x", "y", "loss_mask", "pos", "disp", "stress_vm_raw")
+
+
+class Data:
+    """Attribute bag for one graph (stand-in for ``torch_geometric.data.Data``, ``dataset.py:266-277``)."""
+
+    def __init__(self, **kwargs: Any):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def keys(self):
+        return [k for k in self.__dict__ if not k.startswith("_")]
+
+    def to_dict(self) -> dict:
+        return {k: getattr(self, k) for k in self.keys()}
+
+    @property
+    def num_nodes(self) -> int:
+        x = getattr(self, "x", None)
+        if x is not None:
+            return int(x.shape[0])
+        ei = getattr(self, "edge_index", None)
+        return int(ei.max()) + 1 if ei is not None and ei.numel() else 0
+
+    @property
+    def num_edges(self) -> int:
+        ei = getattr(self, "edge_index", None)
+        return int(ei.shape[1]) if ei is not None else 0
+
+    def _apply(self, fn):
+        out = self.__class__.__new__(self.__class__)
+        for k, v in self.__dict__.items():
+            out.__dict__[k] = fn(v) if isinstance(v, torch.Tensor) else v
+        return out
+
+    def to(self, device, non_blocking: bool = False):
+        return self._apply(lambda t: t.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self):
+        return self._apply(lambda t: t.pin_memory())
+
+    def cuda(self, device=None, non_blocking: bool = False):
+        return self.to(torch.device("cuda", device) if isinstance(device, int) else (device or "cuda"), non_blocking)
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def __repr__(self) -> str:
+        parts = []
+        for k in self.keys():
+            v = getattr(self, k)
+            parts.append(f"{k}={list(v.shape)}" if isinstance(v, torch.Tensor) else f"{k}={v!r}")
+        return f"{self.__class__.__name__}({', '.join(parts)})"
+
+
+class Batch(Data):
+    """Disjoint union of graphs (PyG ``Batch.from_data_list`` semantics)."""
+
+    @classmethod
+    def from_data_list(cls, data_list: Sequence[Data], pin: bool = False) -> "Batch":
+        if len(data_list) == 0:
+            raise ValueError("empty batch")
+        sizes = [d.num_nodes for d in data_list]
+        ptr = torch.zeros(len(sizes) + 1, dtype=torch.int64)
+        ptr[1:] = torch.tensor(sizes, dtype=torch.int64).cumsum(0)
+        out = cls()
+        first = data_list[0]
+        for k in first.keys():
+            v0 = getattr(first, k)
+            vals = [getattr(d, k, None) for d in data_list]
+            if k == "edge_index":
+                dev = v0.device
+                shifted = [v + int(ptr[i]) for i, v in enumerate(vals)]
+                val = torch.cat(shifted, dim=1)
+            elif isinstance(v0, torch.Tensor) and v0.dim() >= 1 and v0.shape[0] == first.num_nodes and k != "global_params" \
+                    and k != "global_params_raw":
+                val = torch.cat(vals, dim=0)
+            elif isinstance(v0, torch.Tensor):
+                val = torch.stack(vals, dim=0)
+            else:
+                val = list(vals)
+            if pin and isinstance(val, torch.Tensor) and not val.is_cuda:
+                val = val.pin_memory()
+            setattr(out, k, val)
+        dev = first.x.device if getattr(first, "x", None) is not None else "cpu"
+        out.batch = torch.repeat_interleave(torch.arange(len(sizes), device=dev), torch.tensor(sizes, device=dev))
+        out.ptr = ptr.to(dev)
+        if pin and not out.batch.is_cuda:
+            out.batch = out.batch.pin_memory()
+        out.num_graphs = len(data_list)
+        return out
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self.x.shape[0])
+
+
+class DataLoader:
+    """Mini-batches of graphs.  ``DataLoader(dataset, batch_size=4, shuffle=True)`` behaves like the
+    PyG loader the reference uses (``train_gnn.py:150-152``).  Extras: ``device`` (prefetching H2D
+    pipeline from pinned memory), ``rank``/``world_size`` (mesh-level data parallel sharding),
+    ``drop_last``."""
+
+    def __init__(self, dataset: Sequence[Data], batch_size: int = 1, shuffle: bool = False, drop_last: bool = False,
+                 device=None, rank: int = 0, world_size: int = 1, seed: int | None = None, keys: Iterable[str] | None = None):
+        self.dataset = dataset
+        self.batch_size = int(batch_size)
+        self.shuffle = shuffle
+        self.drop_last = drop_last
+        self.device = torch.device(device) if device is not None else None
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.seed = seed
+        self.epoch = 0
+        self.keys = tuple(keys) if keys is not None else None
+        self._copy_stream = None
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = int(epoch)
+
+    def _indices(self) -> list[int]:
+        n = len(self.dataset)
+        if self.shuffle:
+            if self.world_size > 1 or self.seed is not None:
+                g = torch.Generator()
+                g.manual_seed((self.seed if self.seed is not None else 0) + self.epoch)
+                perm = torch.randperm(n, generator=g).tolist()
+            else:
+                perm = torch.randperm(n).tolist()  # global CPU generator, like torch's RandomSampler
+        else:
+            perm = list(range(n))
+        if self.world_size > 1:
+            total = (n + self.world_size - 1) // self.world_size * self.world_size
+            perm = perm + perm[: total - n]  # pad by wrap-around (DistributedSampler contract)
+            perm = perm[self.rank:total:self.world_size]
+        return perm
+
+    def __len__(self) -> int:
+        n = len(self._indices())
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def _select(self, d: Data) -> Data:
+        if self.keys is None:
+            return d
+        return Data(**{k: getattr(d, k) for k in self.keys})
+
+    def _host_batches(self):
+        idx = self._indices()
+        for s in range(0, len(idx), self.batch_size):
+            chunk = idx[s:s + self.batch_size]
+            if self.drop_last and len(chunk) < self.batch_size:
+                break
+            yield [self._select(self.dataset[i]) for i in chunk]
+
+    def __iter__(self):
+        if self.device is None or self.device.type != "cuda":
+            for items in self._host_batches():
+                yield Batch.from_data_list(items)
+            return
+        # prefetching pipeline: collate into pinned memory, async copy on a side stream
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        pending = None
+        for items in self._host_batches():
+            if items and getattr(items[0], "x", None) is not None and items[0].x.is_cuda:
+                nxt, ev = Batch.from_data_list(items), None  # already device resident: collate on the device
+            else:
+                host = Batch.from_data_list(items, pin=True)
+                with torch.cuda.stream(cs):
+                    nxt = host.to(self.device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                nxt._host_keepalive = host
+            if pending is not None:
+                yield self._finish(pending)
+            pending = (nxt, ev)
+        if pending is not None:
+            yield self._finish(pending)
+
+    def _finish(self, pending):
+        batch, ev = pending
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for v in batch.__dict__.values():
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(torch.cuda.current_stream(self.device))
+        return batch

@@ -1,0 +1,189 @@
+"""GraphSAGE model for wing stress prediction - B200-native drop-in.
+
+Mirrors the public surface of the reference's ``src/deep_fem_uav_wing/gnn/model.py``:
+
+* ``GraphSAGEModel(in_channels=10, hidden_channels=128, out_channels=1, num_layers=4, dropout=0.1)``
+  with ``forward(x, edge_index, batch=None)`` and ``predict(data)``        (``model.py:24-112``)
+* ``MaskedMSELoss(reduction)``                                             (``model.py:115-153``)
+* ``compute_metrics(pred, target, mask, log_scale)``                       (``model.py:156-216``)
+* ``SAGEConv(in_channels, out_channels)`` - replaces ``torch_geometric.nn.SAGEConv`` as
+  constructed at ``model.py:63`` (mean aggregation, root weight, bias), parameters
+  ``lin_l.weight / lin_l.bias / lin_r.weight``.
+
+``state_dict`` keys are identical to the reference's, so its checkpoints load here and ours
+load there.  Unlike the reference (``model.py:11-19,219-233``) this module needs no PyTorch
+Geometric.  All arithmetic runs in ``libdfw_b200.so`` (hand-written sm_100a CUDA reached
+through a C ABI); inputs must be CUDA tensors - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+HAS_TORCH_GEOMETRIC = False  # not needed; kept because callers of the reference may probe it
+
+
+def _next_seed() -> int:
+    # CPU generator: follows torch.manual_seed (train_gnn.py:128) without touching the device
+    return int(torch.randint(0, 2**62, (1,)).item())
+
+
+class SAGEConv(nn.Module):
+    r"""``out_i = W_l . mean_{j -> i} x_j + b_l + W_r . x_i``  (PyG ``SAGEConv`` defaults).
+
+    ``forward(x, edge_index)`` returns the pre-normalisation tensor, like PyG's layer.  The
+    CSR of ``edge_index`` is built on the device once per tensor and cached.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.in_channels)
+        nn.init.uniform_(self.lin_l.weight, -bound, bound)
+        nn.init.uniform_(self.lin_r.weight, -bound, bound)
+        if self.lin_l.bias is not None:
+            nn.init.uniform_(self.lin_l.bias, -bound, bound)
+
+    def forward(self, x: torch.Tensor, edge_index) -> torch.Tensor:
+        graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, x.shape[0])
+        return ops.SageConvFn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, None, None, graph, 0.0, 0.0, 0,
+                                    False)
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, aggr=mean"
+
+
+class GraphSAGEModel(nn.Module):
+    """GraphSAGE model for node-level stress prediction (``model.py:24-112``).
+
+    Args:
+        in_channels: Input feature dimension (default: 10)
+        hidden_channels: Hidden layer dimension (default: 128)
+        out_channels: Output dimension (default: 1)
+        num_layers: Number of SAGE layers (default: 4)
+        dropout: Dropout rate (default: 0.1)
+    """
+
+    def __init__(self, in_channels: int = 10, hidden_channels: int = 128, out_channels: int = 1, num_layers: int = 4,
+                 dropout: float = 0.1):
+        super().__init__()
+        if hidden_channels % 4 != 0 or hidden_channels > 256:
+            raise ValueError("dfw_b200: hidden_channels must be a multiple of 4 and <= 256")
+        self.in_channels = in_channels
+        self.hidden_channels = hidden_channels
+        self.out_channels = out_channels
+        self.num_layers = num_layers
+        self.dropout = dropout
+        self.compute_dtype = torch.float32
+
+        self.encoder = nn.Sequential(
+            nn.Linear(in_channels, 64), nn.ReLU(), nn.Linear(64, hidden_channels), nn.ReLU()
+        )
+        self.convs = nn.ModuleList()
+        self.norms = nn.ModuleList()
+        for _ in range(num_layers):
+            self.convs.append(SAGEConv(hidden_channels, hidden_channels))
+            self.norms.append(nn.LayerNorm(hidden_channels))
+        self.decoder = nn.Sequential(
+            nn.Linear(hidden_channels, 64), nn.ReLU(), nn.Dropout(dropout), nn.Linear(64, out_channels)
+        )
+
+    def set_compute_dtype(self, dtype: torch.dtype) -> "GraphSAGEModel":
+        """fp32 (default) or bf16 activations; parameters stay fp32 master copies."""
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("compute dtype must be torch.float32 or torch.bfloat16")
+        self.compute_dtype = dtype
+        return self
+
+    def forward(self, x, edge_index, batch=None):
+        """``x [N, in_channels]``, ``edge_index [2, E]`` int64 -> ``[N, out_channels]``.
+        ``batch`` is accepted and ignored, as in the reference (``model.py:74``)."""
+        ops._require_cuda(x, "x")
+        graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, x.shape[0])
+        cd = self.compute_dtype
+        out_dtype = x.dtype
+        h = ops.cast(x, cd) if x.dtype != cd else x
+        p = float(self.dropout) if self.training else 0.0
+        seed = _next_seed() if p > 0.0 else 0
+
+        enc0, enc2 = self.encoder[0], self.encoder[2]
+        h = ops.LinearFn.apply(h, enc0.weight, enc0.bias, True, 0.0, 0)
+        h = ops.LinearFn.apply(h, enc2.weight, enc2.bias, True, 0.0, 0)
+
+        for i, (conv, norm) in enumerate(zip(self.convs, self.norms)):
+            h = ops.SageConvFn.apply(h, conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, norm.weight, norm.bias, graph,
+                                     float(norm.eps), p, seed + 0x632BE5AB * (i + 1), True)
+
+        dec0, dec3 = self.decoder[0], self.decoder[3]
+        if self.out_channels == 1:
+            out = ops.DecoderTailFn.apply(h, dec0.weight, dec0.bias, dec3.weight, dec3.bias, p, seed + 0x7F4A7C15)
+        else:
+            hid = ops.LinearFn.apply(h, dec0.weight, dec0.bias, True, p, seed + 0x7F4A7C15)
+            out = ops.LinearFn.apply(hid, dec3.weight, dec3.bias, False, 0.0, 0)
+        if out.dtype != out_dtype:
+            out = ops.cast(out, out_dtype) if out_dtype in (torch.float32, torch.bfloat16) else out.to(out_dtype)
+        return out
+
+    def predict(self, data):
+        """Convenience method for inference (``model.py:101-112``)."""
+        self.eval()
+        with torch.no_grad():
+            return self.forward(data.x, data.edge_index, getattr(data, "batch", None))
+
+
+class MaskedMSELoss(nn.Module):
+    """MSE loss with masking support for the root singularity band (``model.py:115-153``).
+
+    One fused reduction kernel replaces the boolean indexing, so by default there is no host
+    sync.  With an all-False mask the value is 0 as in the reference; the reference returns a
+    fresh leaf there (no gradient reaches the model), here the gradient is exactly zero.  Pass
+    ``strict_empty=True`` to reproduce the fresh-leaf behaviour (costs one host sync).
+    """
+
+    def __init__(self, reduction: str = "mean", strict_empty: bool = False):
+        super().__init__()
+        if reduction not in ("mean", "sum"):
+            raise ValueError(f"reduction must be 'mean' or 'sum', got {reduction!r}")  # F.mse_loss accepts 'none' too;
+        self.reduction = reduction                                                         # the reference never uses it
+        self.strict_empty = strict_empty
+        self.last_count = None
+
+    def forward(self, pred, target, mask=None):
+        loss, count = ops.MaskedMSEFn.apply(pred, target, mask, self.reduction == "mean")
+        self.last_count = count
+        if self.strict_empty and mask is not None and float(count.item()) == 0.0:
+            return torch.tensor(0.0, device=pred.device, requires_grad=True)
+        return loss
+
+
+def compute_metrics(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor | None = None,
+                    log_scale: bool = True) -> dict:
+    """MAE / RMSE / max error in the original scale for all and masked nodes (``model.py:156-216``).
+    Host-side numpy on purpose, exactly like the reference (not on the hot path)."""
+    p = pred.detach().float().cpu().numpy().flatten()
+    t = target.detach().float().cpu().numpy().flatten()
+    m = mask.detach().cpu().numpy().flatten() if mask is not None else None
+    if log_scale:
+        p, t = np.expm1(p), np.expm1(t)
+
+    def subset(pp, tt, mm):
+        if mm is not None:
+            pp, tt = pp[mm], tt[mm]
+        if len(pp) == 0:
+            return {"mae": 0.0, "rmse": 0.0, "max_error": 0.0, "count": 0}
+        err = np.abs(pp - tt)
+        return {"mae": float(np.mean(err)), "rmse": float(np.sqrt(np.mean(err**2))), "max_error": float(np.max(err)),
+                "count": int(len(pp))}
+
+    return {"all_nodes": subset(p, t, None), "masked_nodes": subset(p, t, m)}

@@ -1,0 +1,439 @@
+"""Tensor-level wrappers and autograd Functions over the C ABI (``libdfw_b200.so``).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every
+arithmetic step of the GraphSAGE path is a hand-written sm_100a kernel reached through
+``_cabi.lib``.  CUDA tensors only - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _cabi
+from ._cabi import DFW_BF16, DFW_F32, EP_DROPOUT, EP_LAYERNORM, EP_RELU, EP_RESIDUAL, check, lib
+
+_DTYPES = {torch.float32: DFW_F32, torch.bfloat16: DFW_BF16}
+LAUNCH_COUNTER = {"kernels": 0}  # kernels launched through the C ABI (bench.py's gpu_launches)
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"dfw_b200 supports float32 and bfloat16 activations, got {t.dtype}") from None
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} must be a CUDA tensor (got device {t.device}): deep_fem_uav_wing.gnn is the B200-native "
+            "implementation and has no CPU fallback."
+        )
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# (a) CSR
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class CSRGraph:
+    """Device-resident canonical CSR of an ``edge_index`` (by destination) and, lazily, its
+    transpose (by source) for the backward pass."""
+
+    edge_index: torch.Tensor | None
+    num_nodes: int
+    num_edges: int
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    inv_deg: torch.Tensor
+    perm: torch.Tensor | None = None
+    status: torch.Tensor | None = None
+    rowptr_t: torch.Tensor | None = None
+    col_t: torch.Tensor | None = None
+    _pending: list = field(default_factory=list)
+
+    def transpose(self):
+        if self.rowptr_t is None:
+            if self.edge_index is None:
+                raise RuntimeError("CSRGraph: transposed CSR was not pre-built and edge_index is gone")
+            rp, col, _, _, st = csr_build_raw(self.edge_index, self.num_nodes, by_src=True, want_perm=False, want_inv_deg=False)
+            self.rowptr_t, self.col_t = rp, col
+        return self.rowptr_t, self.col_t
+
+    def check(self) -> None:
+        """Synchronously validate (raises IndexError on out-of-range endpoints)."""
+        bad = int(self.status[0].item())
+        if bad:
+            raise IndexError(f"edge_index has {bad} edge(s) with an endpoint outside [0, {self.num_nodes})")
+
+    @property
+    def max_degree(self) -> int:
+        return int(self.status[1].item())
+
+
+def csr_build_raw(edge_index: torch.Tensor, num_nodes: int, by_src: bool = False, want_perm: bool = True,
+                  want_inv_deg: bool = True):
+    _require_cuda(edge_index, "edge_index")
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError(f"edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
+    if edge_index.dtype != torch.int64:
+        raise TypeError(f"edge_index must be int64 (torch.long), got {edge_index.dtype}")
+    ei = edge_index.contiguous()
+    E, N = int(ei.shape[1]), int(num_nodes)
+    if E >= 2**31 - 1 or N >= 2**31 - 1:
+        raise ValueError("dfw_b200 uses int32 CSR indices: E and N must be < 2^31")
+    dev = ei.device
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev) if want_perm else None
+    inv_deg = torch.empty(N, dtype=torch.float32, device=dev) if want_inv_deg else None
+    status = torch.empty(2, dtype=torch.int32, device=dev)
+    ws_bytes = lib.dfw_csr_ws_bytes(E, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dfw_csr_build(ei.data_ptr(), E, N, int(by_src), rowptr.data_ptr(), _ptr(col), _ptr(perm), _ptr(inv_deg),
+                                status.data_ptr(), ws.data_ptr(), ws_bytes, _stream(ei)))
+    LAUNCH_COUNTER["kernels"] += 7 if E > 0 else 3
+    return rowptr, col, perm, inv_deg, status
+
+
+_CSR_CACHE: "OrderedDict[tuple, CSRGraph]" = OrderedDict()
+_CSR_CACHE_SIZE = 64
+
+
+def _cache_key(edge_index: torch.Tensor, num_nodes: int):
+    return (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device.index, int(num_nodes))
+
+
+def get_graph(edge_index: torch.Tensor, num_nodes: int, validate: bool | None = None, want_perm: bool = False) -> CSRGraph:
+    """CSR for ``edge_index`` - built once per (tensor identity, version) and cached.
+
+    ``validate``: True = synchronous range check now (one host sync); None/False = the count of bad
+    endpoints stays on the device (``graph.check()`` reads it)."""
+    key = _cache_key(edge_index, num_nodes)
+    g = _CSR_CACHE.get(key)
+    if g is not None and g.edge_index is edge_index:
+        _CSR_CACHE.move_to_end(key)
+        return g
+    rowptr, col, perm, inv_deg, status = csr_build_raw(edge_index, num_nodes, by_src=False, want_perm=want_perm)
+    g = CSRGraph(edge_index, int(num_nodes), int(edge_index.shape[1]), rowptr, col, inv_deg, perm, status)
+    if validate:
+        g.check()
+    _CSR_CACHE[key] = g
+    while len(_CSR_CACHE) > _CSR_CACHE_SIZE:
+        _CSR_CACHE.popitem(last=False)
+    return g
+
+
+def register_graph(edge_index: torch.Tensor, graph: CSRGraph) -> None:
+    """Let a loader attach a pre-built CSR to the ``edge_index`` tensor it hands to the model."""
+    _CSR_CACHE[_cache_key(edge_index, graph.num_nodes)] = graph
+    graph.edge_index = edge_index
+    while len(_CSR_CACHE) > _CSR_CACHE_SIZE:
+        _CSR_CACHE.popitem(last=False)
+
+
+def clear_graph_cache() -> None:
+    _CSR_CACHE.clear()
+
+
+# ----------------------------------------------------------------------------------------------
+# thin kernel wrappers (no autograd)
+# ----------------------------------------------------------------------------------------------
+def aggregate(rowptr, col, row_scale, x, addend=None):
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    N, H = x.shape
+    with torch.cuda.device(x.device):
+        check(lib.dfw_sage_aggregate(rowptr.data_ptr(), col.data_ptr(), _ptr(row_scale), x.data_ptr(),
+                                     _ptr(addend.contiguous() if addend is not None else None), out.data_ptr(), N, H, _dt(x),
+                                     _stream(x)))
+    LAUNCH_COUNTER["kernels"] += 1
+    return out
+
+
+def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=False, residual=None, dropout_p=0.0, seed=0,
+               save_pre=False, rowdot=None, want_out=True):
+    """See ``dfw_linear_fwd``.  ``ln`` = (gamma, beta); ``rowdot`` = (w fp32 [Hout], b fp32 [1] or None)."""
+    _require_cuda(a1, "input")
+    N, k1 = a1.shape
+    Hout = w1.shape[0]
+    dev, dt = a1.device, a1.dtype
+    flags = 0
+    if relu:
+        flags |= EP_RELU
+    if ln is not None:
+        flags |= EP_LAYERNORM
+    if residual is not None:
+        flags |= EP_RESIDUAL
+    if dropout_p > 0.0:
+        flags |= EP_DROPOUT
+    out = torch.empty(N, Hout, dtype=dt, device=dev) if want_out else None
+    pre = torch.empty(N, Hout, dtype=dt, device=dev) if save_pre else None
+    stats = torch.empty(N, 2, dtype=torch.float32, device=dev) if (save_pre and ln is not None) else None
+    rd_out = torch.empty(N, dtype=torch.float32, device=dev) if rowdot is not None else None
+    with torch.cuda.device(dev):
+        check(lib.dfw_linear_fwd(
+            a1.data_ptr(), w1.data_ptr(), k1, _ptr(a2), _ptr(w2), 0 if a2 is None else a2.shape[1], _ptr(bias),
+            _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(eps), _ptr(residual),
+            float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), _ptr(pre), _ptr(stats),
+            _ptr(rowdot[0]) if rowdot is not None else None, _ptr(rowdot[1]) if rowdot is not None else None, _ptr(rd_out),
+            N, Hout, flags, _dt(a1), _stream(a1)))
+    LAUNCH_COUNTER["kernels"] += 1
+    return out, pre, stats, rd_out
+
+
+def epilogue_bwd(g_out, N, Hout, dtype_like, *, g_rowdot=None, rowdot_w=None, pre=None, stats=None, act=None, ln=None,
+                 relu=False, dropout_p=0.0, seed=0):
+    dev = dtype_like.device
+    flags = (EP_RELU if relu else 0) | (EP_LAYERNORM if ln is not None else 0) | (EP_DROPOUT if dropout_p > 0.0 else 0)
+    g_y = torch.empty(N, Hout, dtype=dtype_like.dtype, device=dev)
+    dgamma = dbeta = d_rw = d_rb = None
+    if ln is not None:
+        dgamma = torch.empty(Hout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(Hout, dtype=torch.float32, device=dev)
+    if g_rowdot is not None:
+        d_rw = torch.empty(Hout, dtype=torch.float32, device=dev)
+        d_rb = torch.empty(1, dtype=torch.float32, device=dev)
+    ws_bytes = lib.dfw_epilogue_bwd_ws_bytes(N, Hout)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dfw_epilogue_bwd(
+            _ptr(g_out), _ptr(g_rowdot), _ptr(rowdot_w), _ptr(pre), _ptr(stats), _ptr(act),
+            _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(dropout_p),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, g_y.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(d_rw), _ptr(d_rb), N, Hout, flags,
+            _DTYPES[dtype_like.dtype], ws.data_ptr(), ws_bytes, _stream(dtype_like)))
+    LAUNCH_COUNTER["kernels"] += 2 if (ln is not None or g_rowdot is not None) else 1
+    return g_y, dgamma, dbeta, d_rw, d_rb
+
+
+def linear_bwd_input(g_y, w, row_scale=None, addend=None):
+    N, Hout = g_y.shape
+    K = w.shape[1]
+    g_a = torch.empty(N, K, dtype=g_y.dtype, device=g_y.device)
+    with torch.cuda.device(g_y.device):
+        check(lib.dfw_linear_bwd_input(g_y.data_ptr(), w.data_ptr(), _ptr(row_scale), _ptr(addend), g_a.data_ptr(), N, Hout, K,
+                                       _dt(g_y), _stream(g_y)))
+    LAUNCH_COUNTER["kernels"] += 1
+    return g_a
+
+
+def linear_bwd_weight(g_y, a1, a2=None, want_bias=True):
+    N, Hout = g_y.shape
+    k1 = a1.shape[1]
+    k2 = a2.shape[1] if a2 is not None else 0
+    dev = g_y.device
+    dw1 = torch.empty(Hout, k1, dtype=torch.float32, device=dev)
+    dw2 = torch.empty(Hout, k2, dtype=torch.float32, device=dev) if a2 is not None else None
+    db = torch.empty(Hout, dtype=torch.float32, device=dev) if want_bias else None
+    ws_bytes = lib.dfw_linear_bwd_weight_ws_bytes(N, Hout, k1, k2)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dfw_linear_bwd_weight(g_y.data_ptr(), a1.data_ptr(), k1, _ptr(a2), k2, dw1.data_ptr(), _ptr(dw2), _ptr(db), N,
+                                        Hout, _dt(g_y), 0, ws.data_ptr(), ws_bytes, _stream(g_y)))
+    LAUNCH_COUNTER["kernels"] += 2
+    return dw1, dw2, db
+
+
+def cast(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    if t.dtype == dtype:
+        return t.contiguous()
+    src = t.contiguous()
+    dst = torch.empty_like(src, dtype=dtype)
+    with torch.cuda.device(t.device):
+        check(lib.dfw_cast(src.data_ptr(), _DTYPES[src.dtype], dst.data_ptr(), _DTYPES[dtype], src.numel(), _stream(src)))
+    LAUNCH_COUNTER["kernels"] += 1
+    return dst
+
+
+def _w(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Weight in the compute dtype (detached; fp32 master weights stay in the Parameter)."""
+    return cast(t.detach(), dtype)
+
+
+def _grad_to(param: torch.Tensor, g):
+    if g is None:
+        return None
+    return g if g.dtype == param.dtype else g.to(param.dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd Functions
+# ----------------------------------------------------------------------------------------------
+class SageConvFn(torch.autograd.Function):
+    """SAGEConv forward/backward (mean aggregation + lin_l + lin_r), optionally with the
+    model's LayerNorm -> ReLU -> dropout -> residual tail fused in (``model.py:90-95``)."""
+
+    @staticmethod
+    def forward(ctx, x, w_l, b_l, w_r, gamma, beta, graph: CSRGraph, eps, dropout_p, seed, fused_tail):
+        _require_cuda(x, "x")
+        x = x.contiguous()
+        dt = x.dtype
+        wl, wr = _w(w_l, dt), _w(w_r, dt)
+        bl = _f32(b_l.detach()) if b_l is not None else None
+        agg = aggregate(graph.rowptr, graph.col, graph.inv_deg, x)
+        needs_grad = any(ctx.needs_input_grad[:6])
+        if fused_tail:
+            ln = (_f32(gamma.detach()), _f32(beta.detach()))
+            out, pre, stats, _ = linear_fwd(agg, wl, x, wr, bias=bl, ln=ln, eps=eps, relu=True, residual=x,
+                                            dropout_p=dropout_p, seed=seed, save_pre=needs_grad)
+        else:
+            ln = None
+            out, pre, stats, _ = linear_fwd(agg, wl, x, wr, bias=bl)
+        if needs_grad:
+            ctx.graph = graph
+            ctx.fused_tail, ctx.eps, ctx.dropout_p, ctx.seed = fused_tail, eps, dropout_p, seed
+            ctx.has_bias = b_l is not None
+            ctx.save_for_backward(x, agg, pre, stats, wl, wr, ln[0] if ln else None, ln[1] if ln else None)
+            ctx.param_dtypes = (w_l.dtype, w_r.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, agg, pre, stats, wl, wr, gamma, beta = ctx.saved_tensors
+        graph: CSRGraph = ctx.graph
+        g_out = g_out.contiguous()
+        N, H = g_out.shape
+        dgamma = dbeta = None
+        if ctx.fused_tail:
+            g_y, dgamma, dbeta, _, _ = epilogue_bwd(g_out, N, H, g_out, pre=pre, stats=stats, ln=(gamma, beta), relu=True,
+                                                    dropout_p=ctx.dropout_p, seed=ctx.seed)
+        else:
+            g_y = g_out
+        dwl, dwr, dbl = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias)
+        g_x = None
+        if ctx.needs_input_grad[0]:
+            g_agg = linear_bwd_input(g_y, wl, row_scale=graph.inv_deg)
+            g_root = linear_bwd_input(g_y, wr, addend=g_out if ctx.fused_tail else None)
+            rp_t, col_t = graph.transpose()
+            g_x = aggregate(rp_t, col_t, None, g_agg, addend=g_root)
+        return g_x, dwl, dbl, dwr, dgamma, dbeta, None, None, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """``relu?(x W^T + b)`` (+ dropout): encoder / decoder linears (``model.py:52-57,67-72``)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu, dropout_p, seed):
+        _require_cuda(x, "x")
+        x = x.contiguous()
+        dt = x.dtype
+        wc = _w(w, dt)
+        out, _, _, _ = linear_fwd(x, wc, bias=_f32(b.detach()) if b is not None else None, relu=relu, dropout_p=dropout_p,
+                                  seed=seed)
+        if any(ctx.needs_input_grad[:3]):
+            ctx.relu, ctx.dropout_p, ctx.seed, ctx.has_bias = relu, dropout_p, seed, b is not None
+            ctx.save_for_backward(x, wc, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, wc, act = ctx.saved_tensors
+        g_out = g_out.contiguous()
+        N, H = g_out.shape
+        if ctx.relu or ctx.dropout_p > 0.0:
+            if H % 4 != 0:
+                raise RuntimeError("dfw_b200: ReLU/dropout backward needs out_features % 4 == 0")
+            g_y, _, _, _, _ = epilogue_bwd(g_out, N, H, g_out, act=act, relu=ctx.relu, dropout_p=ctx.dropout_p, seed=ctx.seed)
+        else:
+            g_y = g_out
+        dw, _, db = linear_bwd_weight(g_y, x, None, want_bias=ctx.has_bias)
+        g_x = linear_bwd_input(g_y, wc) if ctx.needs_input_grad[0] else None
+        return g_x, dw, db, None, None, None
+
+
+class DecoderTailFn(torch.autograd.Function):
+    """``Linear(H,64) -> ReLU -> Dropout -> Linear(64,1)`` in one kernel (``model.py:67-72``):
+    the 64 -> 1 projection is a row dot product in the epilogue of the first linear."""
+
+    @staticmethod
+    def forward(ctx, h, w3, b3, w4, b4, dropout_p, seed):
+        _require_cuda(h, "h")
+        h = h.contiguous()
+        dt = h.dtype
+        w3c = _w(w3, dt)
+        w4f = _f32(w4.detach()).reshape(-1)
+        needs_grad = any(ctx.needs_input_grad[:5])
+        b4f = _f32(b4.detach()).reshape(-1) if b4 is not None else None
+        hid, _, _, rd = linear_fwd(h, w3c, bias=_f32(b3.detach()) if b3 is not None else None, relu=True, dropout_p=dropout_p,
+                                   seed=seed, rowdot=(w4f, b4f), want_out=needs_grad)
+        out = rd.unsqueeze(1)
+        if dt != torch.float32:
+            out = cast(out, dt)
+        if needs_grad:
+            ctx.dropout_p, ctx.seed = dropout_p, seed
+            ctx.has_b3, ctx.has_b4 = b3 is not None, b4 is not None
+            ctx.save_for_backward(h, hid, w3c, w4f)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        h, hid, w3c, w4f = ctx.saved_tensors
+        N = h.shape[0]
+        Hmid = hid.shape[1]
+        g_r = g_out.reshape(-1).float().contiguous()
+        g_y, _, _, dw4, db4 = epilogue_bwd(None, N, Hmid, hid, g_rowdot=g_r, rowdot_w=w4f, act=hid, relu=True,
+                                           dropout_p=ctx.dropout_p, seed=ctx.seed)
+        dw3, _, db3 = linear_bwd_weight(g_y, h, None, want_bias=ctx.has_b3)
+        g_h = linear_bwd_input(g_y, w3c) if ctx.needs_input_grad[0] else None
+        return g_h, dw3, db3, dw4.reshape(1, -1), (db4 if ctx.has_b4 else None), None, None
+
+
+class MaskedMSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, reduction_mean):
+        _require_cuda(pred, "pred")
+        pred_c = pred.contiguous()
+        target_c = target.to(pred.dtype).contiguous()
+        N = pred_c.shape[0]
+        C = pred_c.numel() // max(N, 1) if N > 0 else 1
+        m = None
+        if mask is not None:
+            m = mask.reshape(-1).to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.reshape(-1).contiguous()
+            if mask.dtype == torch.bool:
+                m = mask.reshape(-1).contiguous().view(torch.uint8)
+        dev = pred.device
+        result = torch.empty(2, dtype=torch.float32, device=dev)
+        ws_bytes = lib.dfw_masked_mse_ws_bytes(N, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.dfw_masked_mse_fwd(pred_c.data_ptr(), target_c.data_ptr(), _ptr(m), N, C, int(reduction_mean), _dt(pred_c),
+                                         result.data_ptr(), ws.data_ptr(), ws_bytes, _stream(pred_c)))
+        LAUNCH_COUNTER["kernels"] += 1
+        ctx.save_for_backward(pred_c, target_c, m, result)
+        ctx.reduction_mean = reduction_mean
+        ctx.shape = pred.shape
+        loss, count = result[0], result[1]
+        ctx.mark_non_differentiable(count)
+        return loss, count
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_count):
+        pred_c, target_c, m, result = ctx.saved_tensors
+        N = pred_c.shape[0]
+        C = pred_c.numel() // max(N, 1) if N > 0 else 1
+        g = torch.empty_like(pred_c)
+        gl = g_loss.float().reshape(1).contiguous()
+        with torch.cuda.device(pred_c.device):
+            check(lib.dfw_masked_mse_bwd(pred_c.data_ptr(), target_c.data_ptr(), _ptr(m), result.data_ptr(), gl.data_ptr(), N, C,
+                                         int(ctx.reduction_mean), _dt(pred_c), g.data_ptr(), _stream(pred_c)))
+        LAUNCH_COUNTER["kernels"] += 1
+        return g.view(ctx.shape), None, None, None

@@ -1,0 +1,153 @@
+/* dfw_b200.h - C ABI of the B200-native GraphSAGE hot path (libdfw_b200.so).
+ *
+ * Drop-in boundary for Deep-FEM-UAV-Wing's GNN surrogate.  The reference has no FFI of its
+ * own: its boundary is the Python nn.Module contract
+ *     GraphSAGEModel.forward(x, edge_index, batch=None)   src/deep_fem_uav_wing/gnn/model.py:74-99
+ *     SAGEConv(H, H)(h, edge_index)                        model.py:63,90  (torch_geometric, un-vendored)
+ *     MaskedMSELoss.forward(pred, target, mask)            model.py:126-153
+ * and everything below sits UNDER a re-created gnn/model.py with the same names.  Each
+ * entry point cites the reference expression it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch types.  All pointers are DEVICE pointers
+ *    on the current device, contiguous row-major, 16-byte aligned.
+ *  - The caller allocates everything (outputs and workspaces, sizes via *_ws_bytes); the
+ *    library never allocates or frees device memory and keeps no pointer after return.
+ *  - Every call takes the CUDA stream to launch on and is asynchronous with respect to the
+ *    host.  Re-entrant, no global mutable state, safe to call from torch's autograd threads.
+ *  - Return value: 0 = ok, non-zero = error; dfw_last_error() gives the thread-local message.
+ *  - dtype: activations/weights are DFW_F32 or DFW_BF16; bias, LayerNorm affine, statistics,
+ *    inv_deg and all accumulation are fp32.
+ *  - CUDA-only: there is no CPU path behind these symbols.
+ */
+#ifndef DFW_B200_H
+#define DFW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* dfw_stream_t;
+
+enum { DFW_F32 = 0, DFW_BF16 = 1 };
+
+/* epilogue / behaviour flags */
+enum {
+    DFW_EP_RELU = 1,      /* ReLU after (optional) LayerNorm                    model.py:92, :54,:56,:69 */
+    DFW_EP_LAYERNORM = 2, /* row LayerNorm(eps, gamma, beta) before ReLU        model.py:64,91          */
+    DFW_EP_RESIDUAL = 4,  /* out = residual + epilogue(...)                     model.py:95             */
+    DFW_EP_DROPOUT = 8    /* inverted dropout (train only)                      model.py:93, :70        */
+};
+
+const char* dfw_last_error(void);
+int dfw_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (a) edge_index -> CSR.   Replaces PyG's per-call gather/scatter bookkeeping behind
+ *     SAGEConv.forward (call site model.py:90; edge_index int64 [2,E] from gnn/dataset.py:63).
+ *     by_src = 0: rows = destination (edge_index[1]), col = source, sorted by (dst, src, edge id)
+ *                 == numpy.lexsort((src, dst)); used by the forward mean.
+ *     by_src = 1: rows = source, col = destination (transposed CSR) for the backward gather.
+ *     rowptr int32 [N+1], col int32 [E], perm int32 [E] (may be NULL), inv_deg fp32 [N] (may be
+ *     NULL) = 1/max(deg,1).  status int32 [2] (device): [0] = number of out-of-range endpoints
+ *     (the CSR is invalid if non-zero), [1] = max degree.  Requires E, N < 2^31.
+ * ---------------------------------------------------------------------------------------- */
+size_t dfw_csr_ws_bytes(int64_t E, int64_t N);
+int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src,
+                  int32_t* rowptr, int32_t* col, int32_t* perm, float* inv_deg,
+                  int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b) deterministic segmented neighbour aggregation (no atomics):
+ *        out[i,:] = (addend ? addend[i,:] : 0) + (row_scale ? row_scale[i] : 1) * sum_{k in row i} x[col[k],:]
+ *     row_scale = inv_deg  -> PyG mean aggregation (SAGEConv aggr='mean', model.py:63);
+ *     row_scale = NULL with the transposed CSR -> backward of that mean.
+ *     x, addend, out: [N,H] dtype; fp32 accumulation in CSR order.  H*sizeof(dtype) % 16 == 0.
+ * ---------------------------------------------------------------------------------------- */
+int dfw_sage_aggregate(const int32_t* rowptr, const int32_t* col, const float* row_scale,
+                       const void* x, const void* addend, void* out,
+                       int64_t N, int64_t H, int dtype, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (c) fused node-wise linear:
+ *        y   = a1 . w1^T (+ a2 . w2^T) (+ bias)                       [N,Hout]
+ *        out = (residual +) dropout(relu(layernorm(y)))               per `flags`
+ *     SAGEConv: a1 = mean-aggregate, w1 = lin_l.weight, bias = lin_l.bias, a2 = h,
+ *     w2 = lin_r.weight (model.py:90), epilogue = model.py:91-95.  Encoder/decoder linears
+ *     (model.py:52-57,67-72): a2 = NULL.  a1 [N,k1], w1 [Hout,k1], a2 [N,k2], w2 [Hout,k2].
+ *     pre_out (nullable) receives y (saved for backward); ln_stats (nullable) receives
+ *     (mean, rstd) per row [N,2].  rowdot_w (nullable, fp32 [Hout]) with rowdot_out fp32 [N]:
+ *     rowdot_out[i] = sum_c out[i,c]*rowdot_w[c] + *rowdot_b  (decoder's Linear(64,1), model.py:71;
+ *     rowdot_b is a device pointer to one fp32, nullable = 0)
+ *     and `out` may then be NULL.  Dropout keep-mask is a pure function of
+ *     (seed, row*Hout+col): the backward regenerates it.
+ * ---------------------------------------------------------------------------------------- */
+int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1,
+                   const void* a2, const void* w2, int64_t k2,
+                   const float* bias, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                   const void* residual, float dropout_p, uint64_t seed,
+                   void* out, void* pre_out, float* ln_stats,
+                   const float* rowdot_w, const float* rowdot_b, float* rowdot_out,
+                   int64_t N, int64_t Hout, int flags, int dtype, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (d1) backward of the epilogue of (c): given g_out = dL/d out, produce g_y = dL/d y.
+ *      Recomputes xhat/relu mask from pre_out + ln_stats and the dropout mask from seed.
+ *      Without DFW_EP_LAYERNORM, `act` (the saved post-ReLU output) gives the ReLU mask.
+ *      dgamma/dbeta fp32 [Hout] (LayerNorm only).  ws: dfw_epilogue_bwd_ws_bytes.
+ *      rowdot variant: g_rowdot fp32 [N] (dL/d rowdot_out) replaces g_out, and
+ *      d_rowdot_w [Hout], d_rowdot_b [1] are produced.
+ * ---------------------------------------------------------------------------------------- */
+size_t dfw_epilogue_bwd_ws_bytes(int64_t N, int64_t Hout);
+int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const float* rowdot_w,
+                     const void* pre_out, const float* ln_stats, const void* act,
+                     const float* ln_gamma, const float* ln_beta,
+                     float dropout_p, uint64_t seed,
+                     void* g_y, float* dgamma, float* dbeta, float* d_rowdot_w, float* d_rowdot_b,
+                     int64_t N, int64_t Hout, int flags, int dtype,
+                     void* ws, size_t ws_bytes, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (d2) input gradients of (c):   g_a = (row_scale ? row_scale[i] : 1) * (g_y . w) (+ addend)
+ *      g_y [N,Hout], w [Hout,K] -> g_a [N,K].  For SAGEConv: w = lin_l.weight with
+ *      row_scale = inv_deg (then (b) over the transposed CSR finishes the mean's backward), and
+ *      w = lin_r.weight with addend = the residual-path gradient.
+ * ---------------------------------------------------------------------------------------- */
+int dfw_linear_bwd_input(const void* g_y, const void* w, const float* row_scale, const void* addend,
+                         void* g_a, int64_t N, int64_t Hout, int64_t K, int dtype, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (d3) weight gradients of (c):  dW1 = g_y^T . a1  [Hout,k1], dW2 = g_y^T . a2 [Hout,k2],
+ *      dbias = column sums of g_y [Hout] (nullable).  fp32 outputs.  Deterministic split over
+ *      nodes + fixed-order second pass (no float atomics).  `accumulate` != 0 adds into dW/dbias.
+ * ---------------------------------------------------------------------------------------- */
+size_t dfw_linear_bwd_weight_ws_bytes(int64_t N, int64_t Hout, int64_t k1, int64_t k2);
+int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1, const void* a2, int64_t k2,
+                          float* dw1, float* dw2, float* dbias,
+                          int64_t N, int64_t Hout, int dtype, int accumulate,
+                          void* ws, size_t ws_bytes, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Masked MSE (model.py:126-153) without boolean indexing / host sync.
+ *   result fp32 [2]: [0] = loss (mean: sum/max(count,1); sum: sum), [1] = number of selected
+ *   elements.  mask uint8 [N] (nullable = all rows).  pred/target fp32 or bf16 [N,C].
+ *   bwd: g_pred = g_loss * 2 (pred-target) * mask / (mean ? max(count,1) : 1).
+ * ---------------------------------------------------------------------------------------- */
+size_t dfw_masked_mse_ws_bytes(int64_t N, int64_t C);
+int dfw_masked_mse_fwd(const void* pred, const void* target, const uint8_t* mask, int64_t N, int64_t C,
+                       int reduction_mean, int dtype, float* result, void* ws, size_t ws_bytes,
+                       dfw_stream_t stream);
+int dfw_masked_mse_bwd(const void* pred, const void* target, const uint8_t* mask, const float* result,
+                       const float* g_loss, int64_t N, int64_t C, int reduction_mean, int dtype,
+                       void* g_pred, dfw_stream_t stream);
+
+/* dtype conversion helper (weights fp32 -> bf16 copies for the bf16 path) */
+int dfw_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, dfw_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFW_B200_H */
