@@ -113,6 +113,16 @@ class Batch(Data):
     def num_nodes(self) -> int:
         return int(self.x.shape[0])
 
+    def __getattr__(self, name):
+        # `batch` (graph id per node) is derived from `ptr` on first use: the model ignores it
+        # (model.py:74), so the prefetching loader does not ship it over PCIe.
+        if name == "batch" and "ptr" in self.__dict__:
+            ptr = self.__dict__["ptr"]
+            b = torch.repeat_interleave(torch.arange(ptr.numel() - 1, device=ptr.device), ptr[1:] - ptr[:-1])
+            self.__dict__["batch"] = b
+            return b
+        raise AttributeError(name)
+
 
 class DataLoader:
     """Mini-batches of graphs.  ``DataLoader(dataset, batch_size=4, shuffle=True)`` behaves like the
@@ -175,32 +185,125 @@ class DataLoader:
             for items in self._host_batches():
                 yield Batch.from_data_list(items)
             return
-        # prefetching pipeline: collate into pinned memory, async copy on a side stream
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=self.device)
-        cs = self._copy_stream
-        pending = None
-        for items in self._host_batches():
-            if items and getattr(items[0], "x", None) is not None and items[0].x.is_cuda:
-                nxt, ev = Batch.from_data_list(items), None  # already device resident: collate on the device
-            else:
-                host = Batch.from_data_list(items, pin=True)
-                with torch.cuda.stream(cs):
-                    nxt = host.to(self.device, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(cs)
-                nxt._host_keepalive = host
-            if pending is not None:
-                yield self._finish(pending)
-            pending = (nxt, ev)
-        if pending is not None:
-            yield self._finish(pending)
+        first = self.dataset[0] if len(self.dataset) else None
+        if first is not None and getattr(first, "x", None) is not None and first.x.is_cuda:
+            for items in self._host_batches():  # device-resident dataset: collate on the device
+                yield Batch.from_data_list(items)
+            return
+        yield from self._prefetch_iter()
 
-    def _finish(self, pending):
-        batch, ev = pending
-        if ev is not None:
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            for v in batch.__dict__.values():
-                if isinstance(v, torch.Tensor) and v.is_cuda:
-                    v.record_stream(torch.cuda.current_stream(self.device))
-        return batch
+    # -- host -> device pipeline ---------------------------------------------------------------
+    # A worker thread collates each batch straight into reusable pinned staging buffers and issues
+    # the H2D copies on a side stream; the consumer only waits on the copy's event.  Two staging
+    # slots => the copy of batch i+1 overlaps the compute of batch i.
+    def _prefetch_iter(self):
+        import queue
+        import threading
+
+        dev = self.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        q: "queue.Queue" = queue.Queue(maxsize=2)
+        slots = [_StagingSlot() for _ in range(3)]
+        stop = threading.Event()
+
+        def worker():
+            try:
+                torch.cuda.set_device(dev)
+                for n, items in enumerate(self._host_batches()):
+                    if stop.is_set():
+                        return
+                    slot = slots[n % len(slots)]
+                    if slot.event is not None:
+                        slot.event.synchronize()  # previous copy out of this slot has finished
+                    host = slot.collate(items)
+                    with torch.cuda.stream(cs):
+                        out = Batch()
+                        for k, v in host.items():
+                            setattr(out, k, v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v)
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
+                    slot.event = ev
+                    out.num_graphs = len(items)
+                    q.put((out, ev))
+                q.put(None)
+            except BaseException as e:  # surface worker failures in the consumer
+                q.put(e)
+
+        th = threading.Thread(target=worker, daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                batch, ev = item
+                cur = torch.cuda.current_stream(dev)
+                cur.wait_event(ev)
+                for v in batch.__dict__.values():
+                    if isinstance(v, torch.Tensor) and v.is_cuda:
+                        v.record_stream(cur)
+                yield batch
+        finally:
+            stop.set()
+            while th.is_alive():
+                try:
+                    q.get_nowait()
+                except Exception:
+                    pass
+                th.join(timeout=0.05)
+
+
+class _StagingSlot:
+    """Reusable pinned host buffers for one in-flight batch."""
+
+    def __init__(self):
+        self.bufs: dict[str, torch.Tensor] = {}
+        self.event = None
+
+    def _buf(self, key, shape, dtype):
+        need = 1
+        for s_ in shape:
+            need *= int(s_)
+        b = self.bufs.get(key)
+        if b is None or b.numel() < need or b.dtype != dtype:
+            b = torch.empty(max(need, 1) * 5 // 4, dtype=dtype).pin_memory()
+            self.bufs[key] = b
+        return b[:need].view(shape)
+
+    def collate(self, items):
+        first = items[0]
+        sizes = [d.num_nodes for d in items]
+        out = {}
+        for k in first.keys():
+            v0 = getattr(first, k)
+            vals = [getattr(d, k) for d in items]
+            if k == "edge_index":
+                e_tot = sum(int(v.shape[1]) for v in vals)
+                buf = self._buf(k, (2, e_tot), v0.dtype)
+                off_n = off_e = 0
+                for v, n in zip(vals, sizes):
+                    e = int(v.shape[1])
+                    torch.add(v, off_n, out=buf[:, off_e:off_e + e])
+                    off_n += n
+                    off_e += e
+                out[k] = buf
+            elif isinstance(v0, torch.Tensor) and v0.dim() >= 1 and v0.shape[0] == first.num_nodes and k not in ("global_params", "global_params_raw"):
+                shape = (sum(sizes),) + tuple(v0.shape[1:])
+                buf = self._buf(k, shape, v0.dtype)
+                torch.cat(vals, dim=0, out=buf)
+                out[k] = buf
+            elif isinstance(v0, torch.Tensor):
+                buf = self._buf(k, (len(vals),) + tuple(v0.shape), v0.dtype)
+                torch.stack(vals, dim=0, out=buf)
+                out[k] = buf
+            else:
+                out[k] = list(vals)
+        ptr = self._buf("ptr", (len(sizes) + 1,), torch.int64)
+        ptr[0] = 0
+        ptr[1:] = torch.tensor(sizes, dtype=torch.int64).cumsum(0)
+        out["ptr"] = ptr
+        return out

@@ -113,7 +113,7 @@ class GraphSAGEModel(nn.Module):
         graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, x.shape[0])
         cd = self.compute_dtype
         out_dtype = x.dtype
-        h = ops.cast(x, cd) if x.dtype != cd else x
+        h = ops.cast_ad(x, cd)
         p = float(self.dropout) if self.training else 0.0
         seed = _next_seed() if p > 0.0 else 0
 
@@ -131,9 +131,7 @@ class GraphSAGEModel(nn.Module):
         else:
             hid = ops.LinearFn.apply(h, dec0.weight, dec0.bias, True, p, seed + 0x7F4A7C15)
             out = ops.LinearFn.apply(hid, dec3.weight, dec3.bias, False, 0.0, 0)
-        if out.dtype != out_dtype:
-            out = ops.cast(out, out_dtype) if out_dtype in (torch.float32, torch.bfloat16) else out.to(out_dtype)
-        return out
+        return ops.cast_ad(out, out_dtype)
 
     def predict(self, data):
         """Convenience method for inference (``model.py:101-112``)."""

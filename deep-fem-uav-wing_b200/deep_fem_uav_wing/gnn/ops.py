@@ -18,6 +18,52 @@ _DTYPES = {torch.float32: DFW_F32, torch.bfloat16: DFW_BF16}
 LAUNCH_COUNTER = {"kernels": 0}  # kernels launched through the C ABI (bench.py's gpu_launches)
 
 
+class KernelProfiler:
+    """Optional per-call CUDA-event timing of the C-ABI launches (bench.py's roofline pass).
+    Events are recorded on the stream the kernels are launched on."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b, nbytes, flops in self.records:
+            r = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            r["calls"] += 1
+            r["ms"] += a.elapsed_time(b)
+            r["bytes"] += nbytes
+            r["flops"] += flops
+        return out
+
+
+PROFILER: KernelProfiler | None = None
+
+
+class _prof:
+    __slots__ = ("name", "nbytes", "flops", "a")
+
+    def __init__(self, name, nbytes=0, flops=0):
+        self.name, self.nbytes, self.flops = name, nbytes, flops
+
+    def __enter__(self):
+        if PROFILER is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILER is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            PROFILER.records.append((self.name, self.a, b, self.nbytes, self.flops))
+        return False
+
+
+def _esz(t) -> int:
+    return 4 if t.dtype == torch.float32 else 2
+
+
 def _dt(t: torch.Tensor) -> int:
     try:
         return _DTYPES[t.dtype]
@@ -107,7 +153,7 @@ def csr_build_raw(edge_index: torch.Tensor, num_nodes: int, by_src: bool = False
     status = torch.empty(2, dtype=torch.int32, device=dev)
     ws_bytes = lib.dfw_csr_ws_bytes(E, N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _prof("csr_build", 16 * E + 4 * E + 4 * (N + 1)):
         check(lib.dfw_csr_build(ei.data_ptr(), E, N, int(by_src), rowptr.data_ptr(), _ptr(col), _ptr(perm), _ptr(inv_deg),
                                 status.data_ptr(), ws.data_ptr(), ws_bytes, _stream(ei)))
     LAUNCH_COUNTER["kernels"] += 7 if E > 0 else 3
@@ -162,7 +208,9 @@ def aggregate(rowptr, col, row_scale, x, addend=None):
     x = x.contiguous()
     out = torch.empty_like(x)
     N, H = x.shape
-    with torch.cuda.device(x.device):
+    E = col.shape[0]
+    amin = (2 + (addend is not None)) * N * H * _esz(x) + 4 * E + 4 * (N + 1)
+    with torch.cuda.device(x.device), _prof("aggregate", amin):
         check(lib.dfw_sage_aggregate(rowptr.data_ptr(), col.data_ptr(), _ptr(row_scale), x.data_ptr(),
                                      _ptr(addend.contiguous() if addend is not None else None), out.data_ptr(), N, H, _dt(x),
                                      _stream(x)))
@@ -190,7 +238,12 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=Fals
     pre = torch.empty(N, Hout, dtype=dt, device=dev) if save_pre else None
     stats = torch.empty(N, 2, dtype=torch.float32, device=dev) if (save_pre and ln is not None) else None
     rd_out = torch.empty(N, dtype=torch.float32, device=dev) if rowdot is not None else None
-    with torch.cuda.device(dev):
+    k2 = 0 if a2 is None else a2.shape[1]
+    es = _esz(a1)
+    nbytes = N * (k1 + k2) * es + (N * Hout * es if (residual is not None and residual is not a2) else 0) \
+        + N * Hout * es * (int(want_out) + int(save_pre)) + (8 * N if stats is not None else 0) + (4 * N if rowdot is not None else 0) \
+        + Hout * (k1 + k2) * es
+    with torch.cuda.device(dev), _prof("linear_fwd", nbytes, 2 * N * Hout * (k1 + k2)):
         check(lib.dfw_linear_fwd(
             a1.data_ptr(), w1.data_ptr(), k1, _ptr(a2), _ptr(w2), 0 if a2 is None else a2.shape[1], _ptr(bias),
             _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(eps), _ptr(residual),
@@ -215,7 +268,9 @@ def epilogue_bwd(g_out, N, Hout, dtype_like, *, g_rowdot=None, rowdot_w=None, pr
         d_rb = torch.empty(1, dtype=torch.float32, device=dev)
     ws_bytes = lib.dfw_epilogue_bwd_ws_bytes(N, Hout)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    es = 4 if dtype_like.dtype == torch.float32 else 2
+    nbytes = N * Hout * es * (1 + int(g_out is not None) + int(pre is not None) + int(act is not None)) + (8 * N if stats is not None else 0)
+    with torch.cuda.device(dev), _prof("epilogue_bwd", nbytes):
         check(lib.dfw_epilogue_bwd(
             _ptr(g_out), _ptr(g_rowdot), _ptr(rowdot_w), _ptr(pre), _ptr(stats), _ptr(act),
             _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(dropout_p),
@@ -229,7 +284,8 @@ def linear_bwd_input(g_y, w, row_scale=None, addend=None):
     N, Hout = g_y.shape
     K = w.shape[1]
     g_a = torch.empty(N, K, dtype=g_y.dtype, device=g_y.device)
-    with torch.cuda.device(g_y.device):
+    nbytes = (N * Hout + N * K * (1 + int(addend is not None)) + Hout * K) * _esz(g_y)
+    with torch.cuda.device(g_y.device), _prof("linear_bwd_input", nbytes, 2 * N * Hout * K):
         check(lib.dfw_linear_bwd_input(g_y.data_ptr(), w.data_ptr(), _ptr(row_scale), _ptr(addend), g_a.data_ptr(), N, Hout, K,
                                        _dt(g_y), _stream(g_y)))
     LAUNCH_COUNTER["kernels"] += 1
@@ -246,7 +302,8 @@ def linear_bwd_weight(g_y, a1, a2=None, want_bias=True):
     db = torch.empty(Hout, dtype=torch.float32, device=dev) if want_bias else None
     ws_bytes = lib.dfw_linear_bwd_weight_ws_bytes(N, Hout, k1, k2)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    nbytes = N * (Hout + k1 + k2) * _esz(g_y) + 4 * Hout * (k1 + k2)
+    with torch.cuda.device(dev), _prof("linear_bwd_weight", nbytes, 2 * N * Hout * (k1 + k2)):
         check(lib.dfw_linear_bwd_weight(g_y.data_ptr(), a1.data_ptr(), k1, _ptr(a2), k2, dw1.data_ptr(), _ptr(dw2), _ptr(db), N,
                                         Hout, _dt(g_y), 0, ws.data_ptr(), ws_bytes, _stream(g_y)))
     LAUNCH_COUNTER["kernels"] += 2
@@ -262,6 +319,23 @@ def cast(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         check(lib.dfw_cast(src.data_ptr(), _DTYPES[src.dtype], dst.data_ptr(), _DTYPES[dtype], src.numel(), _stream(src)))
     LAUNCH_COUNTER["kernels"] += 1
     return dst
+
+
+class CastFn(torch.autograd.Function):
+    """dtype conversion that stays on the autograd tape (bf16 activations <-> fp32 boundary)."""
+
+    @staticmethod
+    def forward(ctx, t, dtype):
+        ctx.src_dtype = t.dtype
+        return cast(t, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return cast(g, ctx.src_dtype), None
+
+
+def cast_ad(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    return t if t.dtype == dtype else CastFn.apply(t, dtype)
 
 
 def _w(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:

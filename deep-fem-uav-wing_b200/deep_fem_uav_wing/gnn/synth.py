@@ -146,8 +146,9 @@ def surface_tri_wing(n_nodes: int, seed: int = 42, shuffle_edges: bool = True, p
     # area-weighted vertex normals (fem.py:390-424 does the same on the real surface)
     fn = np.cross(pos[faces[:, 1]] - pos[faces[:, 0]], pos[faces[:, 2]] - pos[faces[:, 0]])
     normal = np.zeros_like(pos)
-    for k in range(3):
-        np.add.at(normal, faces[:, k], fn)
+    for c in range(3):
+        for k in range(3):
+            normal[:, c] += np.bincount(faces[:, k], weights=fn[:, c], minlength=n)
     und = faces_to_undirected(faces, n)
     stress = _synthetic_stress(pos, p, rng)
     span = float(pos[:, 1].max() - pos[:, 1].min())

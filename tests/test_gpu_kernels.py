@@ -1,0 +1,216 @@
+"""Kernel-level parity (GPU, through the C ABI): CSR build bit-exact, aggregation, linear pieces."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import TOL_BF16, TOL_FP32, rel_l2, rel_max
+from oracle import csr_aggregate_c, csr_oracle_c
+from oracle.sage_oracle import csr_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from deep_fem_uav_wing.gnn import ops as _ops
+
+    return _ops
+
+
+def _check_csr(ops, ei_np, n, by_src):
+    ei = torch.from_numpy(ei_np).cuda()
+    rowptr, col, perm, inv, status = ops.csr_build_raw(ei, n, by_src=by_src)
+    o = csr_oracle_c(ei_np, n, "src" if by_src else "dst")
+    assert int(status[0]) == 0
+    assert torch.equal(rowptr.cpu(), torch.from_numpy(o[0]))
+    assert torch.equal(col.cpu(), torch.from_numpy(o[1]))
+    assert torch.equal(perm.cpu(), torch.from_numpy(o[2]))
+    assert torch.equal(inv.cpu(), torch.from_numpy(o[3]))  # 1/max(deg,1): correctly rounded on both sides
+    deg = np.diff(o[0])
+    assert int(status[1]) == (int(deg.max()) if n else 0)
+
+
+@pytest.mark.parametrize("by_src", [False, True])
+def test_csr_bit_exact_random_and_edge_cases(ops, by_src):
+    rng = np.random.default_rng(0)
+    for n, e in ((1, 0), (7, 0), (1, 5), (50, 400), (1000, 20000), (5000, 5001), (4097, 100000)):
+        ei = rng.integers(0, n, size=(2, e)).astype(np.int64)  # duplicates and self loops included
+        _check_csr(ops, ei, n, by_src)
+
+
+def test_csr_bit_exact_high_degree_rows(ops):
+    rng = np.random.default_rng(1)
+    # star with 6000 leaves (row longer than the 4096-key shared-memory sort), a 3000-row and a 33-row
+    src = np.concatenate([np.arange(1, 6001), rng.integers(0, 7000, 3000), rng.integers(0, 7000, 33), rng.integers(0, 7000, 20000)])
+    dst = np.concatenate([np.zeros(6000, np.int64), np.full(3000, 5), np.full(33, 9), rng.integers(0, 7000, 20000)])
+    order = rng.permutation(src.size)
+    ei = np.stack([src[order], dst[order]]).astype(np.int64)
+    _check_csr(ops, ei, 7000, False)
+    _check_csr(ops, ei, 7000, True)
+
+
+def test_csr_bit_exact_on_meshes_and_golden_model_graphs(ops):
+    from deep_fem_uav_wing.gnn import synth
+    from helpers import load_golden
+
+    for m in (synth.surface_tri_wing(20000, seed=42), synth.tet_lattice_wing(20000, seed=42),
+              synth.tet_lattice_wing(5000, seed=1, node_order="random")):
+        _check_csr(ops, m["edge_index"], m["num_nodes"], False)
+        _check_csr(ops, m["edge_index"], m["num_nodes"], True)
+    g = load_golden("model_tet500_h128_l4")
+    _check_csr(ops, g["edge_index"], g["x"].shape[0], False)
+
+
+def test_csr_reports_out_of_range(ops):
+    ei = torch.tensor([[0, 1, 9, -1], [1, 2, 0, 0]], dtype=torch.int64).cuda()
+    g = ops.get_graph(ei, 3)
+    with pytest.raises(IndexError):
+        g.check()
+    with pytest.raises(TypeError):
+        ops.csr_build_raw(ei.int(), 3)
+    with pytest.raises(ValueError):
+        ops.csr_build_raw(ei[0], 3)
+
+
+def test_csr_input_order_invariance(ops):
+    rng = np.random.default_rng(3)
+    n, e = 3000, 30000
+    ei = np.unique(rng.integers(0, n, size=(2, e)), axis=1).astype(np.int64)
+    a = ops.csr_build_raw(torch.from_numpy(ei).cuda(), n)
+    b = ops.csr_build_raw(torch.from_numpy(ei[:, rng.permutation(ei.shape[1])]).cuda(), n)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])  # canonical whatever the edge order
+
+
+@pytest.mark.parametrize("h", [4, 16, 64, 128, 256, 96])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_aggregate_matches_oracle(ops, h, dtype):
+    rng = np.random.default_rng(h)
+    n, e = 3001, 25000
+    ei = rng.integers(0, n, size=(2, e)).astype(np.int64)
+    ei[1, :200] = 7  # one long row
+    if dtype == torch.bfloat16 and (h * 2) % 16:
+        pytest.skip("row not 16-byte aligned")
+    x = torch.from_numpy(rng.standard_normal((n, h)).astype(np.float32)).to(dtype)
+    rowptr, col, _, inv = csr_oracle_c(ei, n)
+    ref = torch.from_numpy(csr_aggregate_c(rowptr, col, inv, x.float().numpy()))
+    g = ops.get_graph(torch.from_numpy(ei).cuda(), n)
+    got = ops.aggregate(g.rowptr, g.col, g.inv_deg, x.cuda())
+    tol = TOL_FP32 if dtype == torch.float32 else TOL_BF16
+    assert rel_max(got.float().cpu(), ref) < tol
+    again = ops.aggregate(g.rowptr, g.col, g.inv_deg, x.cuda())
+    assert torch.equal(got, again)  # deterministic: no atomics
+    # sum mode + addend over the transposed CSR
+    rp_t, col_t = g.transpose()
+    ot = csr_oracle_c(ei, n, "src")
+    add = torch.from_numpy(rng.standard_normal((n, h)).astype(np.float32)).to(dtype)
+    ref_t = torch.from_numpy(csr_aggregate_c(ot[0], ot[1], None, x.float().numpy())) + add.float()
+    got_t = ops.aggregate(rp_t, col_t, None, x.cuda(), addend=add.cuda())
+    assert rel_max(got_t.float().cpu(), ref_t) < tol
+
+
+def test_aggregate_properties_at_scale(ops):
+    """Size-independent properties on a config-2-sized batch (4 x 50k nodes, H=128): linearity and
+    permutation equivariance of the mean aggregation, transposed-sum adjointness."""
+    from deep_fem_uav_wing.gnn import synth
+
+    m = synth.tet_lattice_wing(200000, seed=9)
+    n = m["num_nodes"]
+    ei = torch.from_numpy(m["edge_index"]).cuda()
+    g = ops.get_graph(ei, n)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(n, 128, device="cuda", generator=gen)
+    y = torch.randn(n, 128, device="cuda", generator=gen)
+    ax, ay = ops.aggregate(g.rowptr, g.col, g.inv_deg, x), ops.aggregate(g.rowptr, g.col, g.inv_deg, y)
+    axy = ops.aggregate(g.rowptr, g.col, g.inv_deg, 2.0 * x + y)
+    assert rel_max(axy, 2.0 * ax + ay) < TOL_FP32
+    # adjointness: <A x, y> == <x, A^T y> with A^T = transposed sum of inv_deg-scaled rows
+    rp_t, col_t = g.transpose()
+    aty = ops.aggregate(rp_t, col_t, None, y * g.inv_deg[:, None])
+    lhs, rhs = (ax.double() * y.double()).sum().item(), (x.double() * aty.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0)
+    # permutation equivariance
+    perm = torch.randperm(n, device="cuda", generator=gen)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n, device="cuda")
+    g2 = ops.get_graph(inv[ei], n)  # relabel node i -> inv[i]
+    ax2 = ops.aggregate(g2.rowptr, g2.col, g2.inv_deg, x[perm])
+    assert rel_max(ax2, ax[perm]) < TOL_FP32
+
+
+def _ref_linear(a1, w1, a2, w2, b, ln, relu, res):
+    y = a1.double() @ w1.double().T
+    if a2 is not None:
+        y = y + a2.double() @ w2.double().T
+    if b is not None:
+        y = y + b.double()
+    out = y
+    if ln is not None:
+        out = torch.nn.functional.layer_norm(out, (out.shape[1],), ln[0].double(), ln[1].double(), 1e-5)
+    if relu:
+        out = out.relu()
+    if res is not None:
+        out = out + res.double()
+    return y, out
+
+
+@pytest.mark.parametrize("hout,k1,k2", [(64, 10, 0), (128, 64, 0), (64, 64, 64), (128, 128, 128), (256, 256, 256), (16, 16, 16), (64, 128, 0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_fwd_and_bwd_pieces(ops, hout, k1, k2, dtype):
+    torch.manual_seed(hout + k1)
+    n = 777
+    dev = "cuda"
+    a1 = torch.randn(n, k1, device=dev).to(dtype)
+    w1 = (torch.randn(hout, k1, device=dev) / k1**0.5).to(dtype)
+    a2 = torch.randn(n, k2, device=dev).to(dtype) if k2 else None
+    w2 = (torch.randn(hout, k2, device=dev) / k2**0.5).to(dtype) if k2 else None
+    b = torch.randn(hout, device=dev)
+    gamma, beta = torch.rand(hout, device=dev) + 0.5, torch.randn(hout, device=dev)
+    res = torch.randn(n, hout, device=dev).to(dtype) if k2 == hout else None
+    tol = TOL_FP32 if dtype == torch.float32 else TOL_BF16
+    use_ln = k2 > 0
+    out, pre, stats, _ = ops.linear_fwd(a1, w1, a2, w2, bias=b, ln=(gamma, beta) if use_ln else None, relu=True, residual=res,
+                                        save_pre=True)
+    y_ref, out_ref = _ref_linear(a1, w1, a2, w2, b, (gamma, beta) if use_ln else None, True, res)
+    assert rel_max(pre.double(), y_ref) < tol
+    assert rel_max(out.double(), out_ref) < (tol if dtype == torch.float32 else 3 * tol)
+    if use_ln:
+        mean = y_ref.mean(1)
+        rstd = 1.0 / torch.sqrt(y_ref.var(1, unbiased=False) + 1e-5)
+        assert rel_max(stats[:, 0].double(), mean) < max(tol, 1e-5) and rel_max(stats[:, 1].double(), rstd) < max(tol, 1e-5)
+    # dx and dW pieces
+    g = torch.randn(n, hout, device=dev).to(dtype)
+    scale = torch.rand(n, device=dev)
+    add = torch.randn(n, k1, device=dev).to(dtype)
+    dx = ops.linear_bwd_input(g, w1, row_scale=scale, addend=add)
+    dx_ref = scale.double()[:, None] * (g.double() @ w1.double()) + add.double()
+    assert rel_max(dx.double(), dx_ref) < tol
+    dw1, dw2, db = ops.linear_bwd_weight(g, a1, a2)
+    assert rel_l2(dw1.double(), g.double().T @ a1.double()) < tol
+    if k2:
+        assert rel_l2(dw2.double(), g.double().T @ a2.double()) < tol
+    assert rel_l2(db.double(), g.double().sum(0)) < tol
+    dw1b, _, _ = ops.linear_bwd_weight(g, a1, a2)
+    assert torch.equal(dw1, dw1b)  # fixed-order split reduction: bit-reproducible
+
+
+def test_masked_mse_matches_reference_fixture(ops):
+    from helpers import load_golden
+
+    from deep_fem_uav_wing.gnn.model import MaskedMSELoss
+
+    g = load_golden("loss_metrics")
+    targ = torch.from_numpy(g["target"]).cuda()
+    mask = torch.from_numpy(g["mask"]).cuda()
+    for red in ("mean", "sum"):
+        for mname, mm in (("mask", mask), ("none", None), ("allfalse", torch.zeros(50, dtype=torch.bool, device="cuda"))):
+            pred = torch.from_numpy(g["pred"]).cuda().requires_grad_(True)
+            loss = MaskedMSELoss(red)(pred, targ, mm)
+            ref = float(g[f"loss_{red}_{mname}"])
+            assert abs(loss.item() - ref) <= TOL_FP32 * max(1.0, abs(ref))
+            assert loss.requires_grad
+            if mname != "allfalse":
+                loss.backward()
+                assert rel_max(pred.grad.cpu(), g[f"grad_{red}_{mname}"]) < TOL_FP32
+            else:
+                strict = MaskedMSELoss(red, strict_empty=True)(pred, targ, mm)
+                assert strict.item() == 0.0 and strict.requires_grad and strict.grad_fn is None  # fresh leaf (model.py:147-149)
