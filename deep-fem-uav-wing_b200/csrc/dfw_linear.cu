@@ -14,10 +14,22 @@
 #include <algorithm>
 #include <type_traits>
 
+#include <cstdlib>
+
 #include "dfw_common.cuh"
+#include "dfw_linear_tc.cuh"
 
 namespace dfw {
 namespace {
+
+bool force_simt() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFW_FORCE_SIMT");
+        v = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 constexpr int BK = 16;
 constexpr int PAD = 4;
@@ -482,7 +494,7 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
                               const float* bias, const float* ln_gamma, const float* ln_beta, float ln_eps,
                               const void* residual, float dropout_p, uint64_t seed, void* out, void* pre_out,
                               float* ln_stats, const float* rowdot_w, const float* rowdot_b, float* rowdot_out, int64_t N,
-                              int64_t Hout, int flags, int dtype, dfw_stream_t stream) {
+                              int64_t Hout, int flags, int dtype, void* ws, size_t ws_bytes, dfw_stream_t stream) {
     using namespace dfw;
     DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_linear_fwd: unknown dtype %d", dtype);
     DFW_REQUIRE(N >= 0 && Hout >= 1 && Hout <= 256, "dfw_linear_fwd: Hout=%lld must be in [1,256] (N=%lld)",
@@ -496,11 +508,24 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
     DFW_REQUIRE(!(flags & DFW_EP_DROPOUT) || (dropout_p >= 0.f && dropout_p < 1.f), "dfw_linear_fwd: dropout_p=%f not in [0,1)",
                 (double)dropout_p);
     if (N == 0) return 0;
+    if ((flags & DFW_EP_DROPOUT) && dropout_p == 0.f) flags &= ~DFW_EP_DROPOUT;
+    DFW_REQUIRE(!(flags & DFW_EP_LAYERNORM) || (ln_gamma && ln_beta), "dfw_linear_fwd: DFW_EP_LAYERNORM needs gamma and beta");
+    if (ws && !force_simt() && linear_tc_eligible(N, Hout, k1, a2 ? k2 : 0, dtype, a1, a2) &&
+        ws_bytes >= linear_tc_ws_bytes(Hout, k1, a2 ? k2 : 0, dtype) && aligned16(out ? out : a1) &&
+        (!pre_out || aligned16(pre_out)) && (!residual || aligned16(residual))) {
+        tc::Args t{};
+        t.N = N; t.Hout = (int)Hout; t.flags = flags;
+        t.bias = bias; t.gamma = ln_gamma; t.beta = ln_beta; t.eps = ln_eps; t.row_scale = nullptr;
+        t.residual = (flags & DFW_EP_RESIDUAL) ? residual : nullptr;
+        t.drop_thr = dropout_threshold(dropout_p); t.drop_scale = 1.f / (1.f - dropout_p); t.seed = seed;
+        t.out = out; t.pre_out = pre_out; t.ln_stats = ln_stats;
+        t.rowdot_w = rowdot_w; t.rowdot_b = rowdot_b; t.rowdot_out = rowdot_out;
+        return linear_tc_launch(a1, w1, k1, a2, w2, k2, 0, t, dtype, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+    }
     LinArgs a{};
     a.a1 = a1; a.w1 = w1; a.k1 = k1; a.a2 = a2; a.w2 = w2; a.k2 = a2 ? k2 : 0;
     a.bias = bias; a.gamma = ln_gamma; a.beta = ln_beta; a.eps = ln_eps;
     a.residual = (flags & DFW_EP_RESIDUAL) ? residual : nullptr;
-    if ((flags & DFW_EP_DROPOUT) && dropout_p == 0.f) flags &= ~DFW_EP_DROPOUT;
     a.dropout_p = dropout_p; a.drop_thr = dropout_threshold(dropout_p); a.drop_scale = 1.f / (1.f - dropout_p); a.seed = seed;
     a.out = out; a.pre_out = pre_out; a.ln_stats = ln_stats;
     a.rowdot_w = rowdot_w; a.rowdot_b = rowdot_b; a.rowdot_out = rowdot_out;
@@ -511,13 +536,26 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
     return dispatch_cols<__nv_bfloat16, MODE_FWD>(a, Hout, grid_rows(N, 128), grid_rows(N, 128), grid_rows(N, 64), s);
 }
 
+extern "C" size_t dfw_linear_ws_bytes(int64_t Hout, int64_t k1, int64_t k2, int dtype) {
+    if (Hout < 1 || k1 < 1 || k2 < 0) return 0;
+    return dfw::linear_tc_ws_bytes(Hout, k1, k2, dtype);
+}
+
 extern "C" int dfw_linear_bwd_input(const void* g_y, const void* w, const float* row_scale, const void* addend,
-                                    void* g_a, int64_t N, int64_t Hout, int64_t K, int dtype, dfw_stream_t stream) {
+                                    void* g_a, int64_t N, int64_t Hout, int64_t K, int dtype, void* ws, size_t ws_bytes,
+                                    dfw_stream_t stream) {
     using namespace dfw;
     DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_linear_bwd_input: unknown dtype %d", dtype);
     DFW_REQUIRE(N >= 0 && Hout >= 1 && K >= 1, "dfw_linear_bwd_input: bad shape");
     DFW_REQUIRE(g_y && w && g_a, "dfw_linear_bwd_input: null pointer");
     if (N == 0) return 0;
+    if (ws && !force_simt() && linear_tc_eligible(N, K, Hout, 0, dtype, g_y, nullptr) &&
+        ws_bytes >= linear_tc_ws_bytes(K, Hout, 0, dtype) && aligned16(g_a) && (!addend || aligned16(addend))) {
+        tc::Args t{};
+        t.N = N; t.Hout = (int)K; t.flags = addend ? DFW_EP_RESIDUAL : 0;
+        t.row_scale = row_scale; t.residual = addend; t.drop_scale = 1.f; t.out = g_a;
+        return linear_tc_launch(g_y, w, Hout, nullptr, nullptr, 0, 1, t, dtype, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+    }
     LinArgs a{};
     a.a1 = g_y; a.w1 = w; a.row_scale = row_scale; a.addend = addend; a.out = g_a;
     a.N = N; a.Hout = Hout; a.K = K;

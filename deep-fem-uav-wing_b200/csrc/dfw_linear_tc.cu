@@ -1,0 +1,683 @@
+// (c) fused node-wise linear on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+//   y = a1.w1^T (+ a2.w2^T) + bias ; out = residual + dropout(relu(layernorm(row_scale * y)))
+//
+// = SAGEConv's lin_l(mean) + lin_r(h) (PyG; reference call site model.py:90) with the epilogue of
+// model.py:91-95, and - with transposed weights - the input-gradient contraction of the backward.
+//
+// Design (one CTA = one 128-row tile, full output row => LayerNorm stays inside the CTA):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor 2D boxes [128 rows x 128 B] of the activations and
+//              [Hout rows x 128 B] of the weights, SWIZZLE_128B, into a ring of smem stages (mbarrier full/empty)
+//   warp 1   : MMA issuer    - one elected thread issues tcgen05.mma (M=128, N=Hout, K=32 B) with the
+//              accumulator in TMEM; tcgen05.commit releases the stage / signals the epilogue
+//   warps 2-5: epilogue      - tcgen05.ld, one thread per output row: bias, LayerNorm (two-pass, the row
+//              lives in that thread's TMEM lane: no cross-thread reduction), ReLU, dropout, residual, store.
+//              In fp32 mode the same warps first act as CONVERTERS (see below).
+//   bf16 : kind::f16, operands straight from TMA.
+//   fp32 : 3xTF32 error-compensated split (kind::tf32): a = a_hi + a_lo, w = w_hi + w_lo with
+//          x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi);  D += a_lo.w_hi + a_hi.w_lo + a_hi.w_hi.
+//          Per-element error ~2^-22, so results stay inside the 1e-5 fp32 parity bound where a single
+//          TF32 pass (2^-11) would not.  Weights are pre-split by a tiny kernel; the activation split is
+//          done in shared memory, in place, by the converter warps between the TMA and the MMA.
+// Roofline: HBM (intensity 4H/(3b) flop/B is below the tensor ridge for H <= 256): DESIGN.md.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include <cstring>
+
+#include "dfw_common.cuh"
+#include "dfw_linear_tc.cuh"
+
+namespace dfw {
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kChunkBytes = 128;  // one SWIZZLE_128B atom row
+constexpr int kMaxStages = 6;
+
+struct Maps {
+    CUtensorMap a[2];
+    CUtensorMap w_hi[2];
+    CUtensorMap w_lo[2];
+    CUtensorMap out, pre, res;  // [N, Hout] tensors of the epilogue, boxes of [128 rows x 128 B]
+};
+
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    uint32_t spins = 0;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 24)) {  // a legitimate wait lasts microseconds: this is a protocol bug, fail loudly
+            printf("dfw_linear_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+            __trap();
+        }
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows x 128 B = 1024 B)
+// | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+        "[%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void fence_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps only
+
+// One [128 rows x 128 B] box in SWIZZLE_128B layout: 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4).
+// A thread that owns row r touches 8 distinct bank groups per quarter-warp: conflict-free.
+__device__ __forceinline__ uint32_t box_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+// smem carve-up (all offsets from a 1024-aligned base)
+struct Smem {
+    uint32_t a_hi, a_lo, w_hi, w_lo, stage_bytes;
+    uint32_t res, staging, nbuf;  // epilogue regions alias the pipeline stages (free once the last MMA has retired)
+    uint32_t cvec, bars, total;
+};
+__host__ __device__ inline Smem carve(bool tf32, int Npad, int stages, int out_boxes) {
+    Smem s;
+    const uint32_t a = kTileM * kChunkBytes;                                  // 16 KB
+    const uint32_t w = ((uint32_t)Npad * kChunkBytes + 1023u) / 1024u * 1024u;  // Npad rows x 128 B
+    s.a_hi = 0;
+    s.a_lo = a;
+    s.w_hi = tf32 ? 2 * a : a;
+    s.w_lo = s.w_hi + w;
+    s.stage_bytes = tf32 ? 2 * a + 2 * w : a + w;
+    const uint32_t pipe = s.stage_bytes * stages;
+    s.res = 0;
+    s.staging = (uint32_t)out_boxes * a;
+    const uint32_t left = pipe > s.staging ? (pipe - s.staging) / a : 0;
+    s.nbuf = left > 4 ? 4 : left;
+    s.cvec = pipe;
+    s.bars = s.cvec + 4 * 256 * 4;
+    s.total = s.bars + 8 * (3 * kMaxStages + 2) + 16;
+    return s;
+}
+
+template <typename T, bool TF32>
+__global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ Maps maps, const Args p) {
+    constexpr int EPC = kChunkBytes / (int)sizeof(T);  // elements (columns) per 128-byte box: 32 fp32 / 64 bf16
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int out_boxes = p.Hout / EPC;
+    const Smem L = carve(TF32, p.Npad, p.stages, out_boxes);
+    float* cvec = reinterpret_cast<float*>(smem + L.cvec);  // [4][256]: bias, gamma, beta, rowdot_w
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* conv = empty + kMaxStages;
+    uint64_t* accum_full = conv + kMaxStages;
+    uint64_t* res_full = accum_full + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_base = (int64_t)blockIdx.x * kTileM;
+    const int total_chunks = p.chunks[0] + p.chunks[1];
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a[0]);
+        prefetch_tmap(&maps.w_hi[0]);
+        if (p.chunks[1]) {
+            prefetch_tmap(&maps.a[1]);
+            prefetch_tmap(&maps.w_hi[1]);
+        }
+        if (p.out) prefetch_tmap(&maps.out);
+        if (p.pre_out) prefetch_tmap(&maps.pre);
+        if (p.residual) prefetch_tmap(&maps.res);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&conv[s], 128);
+        }
+        mbar_init(accum_full, 1);
+        mbar_init(res_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {  // per-column constants -> smem (read back as broadcasts)
+        for (int c = threadIdx.x - 64; c < p.Hout; c += 128) {
+            cvec[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+            cvec[256 + c] = p.gamma ? __ldg(p.gamma + c) : 1.f;
+            cvec[512 + c] = p.beta ? __ldg(p.beta + c) : 0.f;
+            cvec[768 + c] = p.rowdot_w ? __ldg(p.rowdot_w + c) : 0.f;
+        }
+    }
+    fence_tc_before();
+    __syncthreads();
+    fence_tc_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t stage_tx = (uint32_t)(kTileM * kChunkBytes + p.Npad * kChunkBytes * (TF32 ? 2 : 1));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = 0; c < total_chunks; ++c) {
+                const int seg = c >= p.chunks[0];
+                const int kc = (seg ? c - p.chunks[0] : c) * EPC;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + (size_t)stage * L.stage_bytes;
+                mbar_arrive_expect_tx(&full[stage], stage_tx);
+                tma_load_2d(st + L.a_hi, &maps.a[seg], &full[stage], kc, (int)m_base);
+                tma_load_2d(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0);
+                if (TF32) tma_load_2d(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            if (p.residual) {
+                // the pipeline stages are free once the last MMA has retired: reuse them for the residual tile
+                mbar_wait(accum_full, 0);
+                mbar_arrive_expect_tx(res_full, (uint32_t)(out_boxes * kTileM * kChunkBytes));
+                for (int b = 0; b < out_boxes; ++b)
+                    tma_load_2d(smem + L.res + (size_t)b * kTileM * kChunkBytes, &maps.res, res_full, b * EPC, (int)m_base);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // cute::UMMA::InstrDescriptor: c_format F32 (1<<4) | a/b format (BF16=1, TF32=2) at [7,10)/[10,13) |
+            // K-major A and B | N>>3 at [17,23) | M>>4 at [24,29)
+            const uint32_t fmt = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t accumulate = 0;
+            for (int c = 0; c < total_chunks; ++c) {
+                mbar_wait(TF32 ? &conv[stage] : &full[stage], phase);
+                fence_tc_after();
+                const uint32_t st = smem_u32(smem + (size_t)stage * L.stage_bytes);
+#pragma unroll
+                for (int k = 0; k < kChunkBytes / 32; ++k) {  // UMMA_K = 32 bytes (16 bf16 / 8 tf32)
+                    const uint64_t a_hi = make_desc(st + L.a_hi + k * 32);
+                    const uint64_t w_hi = make_desc(st + L.w_hi + k * 32);
+                    if (TF32) {
+                        const uint64_t a_lo = make_desc(st + L.a_lo + k * 32);
+                        const uint64_t w_lo = make_desc(st + L.w_lo + k * 32);
+                        umma<TF32>(tmem_base, a_lo, w_hi, idesc, accumulate);
+                        umma<TF32>(tmem_base, a_hi, w_lo, idesc, 1u);
+                        umma<TF32>(tmem_base, a_hi, w_hi, idesc, 1u);
+                    } else {
+                        umma<TF32>(tmem_base, a_hi, w_hi, idesc, accumulate);
+                    }
+                    accumulate = 1u;
+                }
+                umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(accum_full);
+        }
+    } else {
+        // ===== converter (fp32 only) then epilogue: warps 2..5 =====
+        const int et = threadIdx.x - 64;  // 0..127
+        if (TF32) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = 0; c < total_chunks; ++c) {
+                mbar_wait(&full[stage], phase);
+                uint8_t* st = smem + (size_t)stage * L.stage_bytes;
+                float4* hi = reinterpret_cast<float4*>(st + L.a_hi);
+                float4* lo = reinterpret_cast<float4*>(st + L.a_lo);
+#pragma unroll
+                for (int i = 0; i < (kTileM * kChunkBytes / 16) / 128; ++i) {  // position-preserving: swizzle-agnostic
+                    const int idx = et + i * 128;
+                    const float4 a = hi[idx];
+                    float4 h, l;
+                    h.x = __uint_as_float(rna_tf32(a.x)); l.x = __uint_as_float(rna_tf32(a.x - h.x));
+                    h.y = __uint_as_float(rna_tf32(a.y)); l.y = __uint_as_float(rna_tf32(a.y - h.y));
+                    h.z = __uint_as_float(rna_tf32(a.z)); l.z = __uint_as_float(rna_tf32(a.z - h.z));
+                    h.w = __uint_as_float(rna_tf32(a.w)); l.w = __uint_as_float(rna_tf32(a.w - h.w));
+                    hi[idx] = h;
+                    lo[idx] = l;
+                }
+                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+                mbar_arrive(&conv[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+
+        mbar_wait(accum_full, 0);
+        fence_tc_after();
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int r_in_tile = q * 32 + lane;
+        const int64_t row = m_base + r_in_tile;
+        const bool rok = row < p.N;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int H = p.Hout;
+        const int n32 = H / 32;
+        const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
+        const bool ln = p.flags & DFW_EP_LAYERNORM;
+        const bool relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
+        const float4* bias4 = reinterpret_cast<const float4*>(cvec);
+        const float4* gam4 = reinterpret_cast<const float4*>(cvec + 256);
+        const float4* bet4 = reinterpret_cast<const float4*>(cvec + 512);
+        const float4* rdw4 = reinterpret_cast<const float4*>(cvec + 768);
+        uint8_t* stg = smem + L.staging;
+        int n_store = 0;  // TMA stores issued so far (staging buffer = n_store % nbuf)
+        float mean = 0.f, rstd = 1.f;
+
+        // y = (acc + bias) * row_scale for 32 columns starting at c0
+        auto load_y = [&](int c0, float* v) {
+            tmem_ld32(t_row + c0, v);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 b = bias4[c0 / 4 + g];
+                v[4 * g] = (v[4 * g] + b.x) * rs;
+                v[4 * g + 1] = (v[4 * g + 1] + b.y) * rs;
+                v[4 * g + 2] = (v[4 * g + 2] + b.z) * rs;
+                v[4 * g + 3] = (v[4 * g + 3] + b.w) * rs;
+            }
+        };
+        // write 32 fp32 values of this thread's row into a staging box (converted to T) at column c_in_box
+        auto stage_row = [&](uint8_t* box, int c_in_box, const float* v) {
+            if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4*>(box + box_off(r_in_tile, c_in_box / 4 + g)) =
+                        make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    Vec16<T> u;
+                    u.from_float(v + 8 * g);
+                    *reinterpret_cast<uint4*>(box + box_off(r_in_tile, c_in_box / 8 + g)) = u.v;
+                }
+            }
+        };
+        auto acquire_box = [&]() -> uint8_t* {
+            // the store that last used this buffer must have finished READING it
+            if (et == 0) {
+                if (L.nbuf >= 4) tma_store_wait_read<3>();
+                else if (L.nbuf == 3) tma_store_wait_read<2>();
+                else if (L.nbuf == 2) tma_store_wait_read<1>();
+                else tma_store_wait_read<0>();
+            }
+            epi_bar();
+            return stg + (size_t)(n_store % L.nbuf) * (kTileM * kChunkBytes);
+        };
+        auto release_box = [&](const CUtensorMap* map, uint8_t* box, int col0) {
+            fence_proxy_async();
+            epi_bar();
+            if (et == 0) {
+                tma_store_2d(map, box, col0, (int)m_base);
+                tma_store_commit();
+            }
+            ++n_store;
+        };
+
+        // ---- pass 1: row sum (LayerNorm mean) and the pre-activation tensor y ----
+        if (ln || p.pre_out) {
+            float s = 0.f;
+            for (int ob = 0; ob < out_boxes; ++ob) {
+                uint8_t* box = p.pre_out ? acquire_box() : nullptr;
+#pragma unroll
+                for (int h = 0; h < EPC / 32; ++h) {
+                    float v[32];
+                    load_y(ob * EPC + h * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s += v[j];
+                    if (p.pre_out) stage_row(box, h * 32, v);
+                }
+                if (p.pre_out) release_box(&maps.pre, box, ob * EPC);
+            }
+            mean = s / (float)H;
+        }
+        // ---- pass 2: variance around the mean (two-pass, like torch) ----
+        if (ln) {
+            float qs = 0.f;
+            for (int cc = 0; cc < n32; ++cc) {
+                float v[32];
+                load_y(cc * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float d = v[j] - mean;
+                    qs = fmaf(d, d, qs);
+                }
+            }
+            rstd = rsqrtf(qs / (float)H + p.eps);
+            if (p.ln_stats && rok) {
+                p.ln_stats[2 * row] = mean;
+                p.ln_stats[2 * row + 1] = rstd;
+            }
+        }
+        // ---- pass 3: normalise, ReLU, dropout, row-dot, residual, store ----
+        if (p.residual) mbar_wait(res_full, 0);
+        float dot = 0.f;
+        for (int ob = 0; ob < out_boxes; ++ob) {
+            uint8_t* box = p.out ? acquire_box() : nullptr;
+            const uint8_t* rbox = smem + L.res + (size_t)ob * kTileM * kChunkBytes;
+#pragma unroll
+            for (int h = 0; h < EPC / 32; ++h) {
+                const int c0 = ob * EPC + h * 32;
+                float v[32];
+                load_y(c0, v);
+                if (ln) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 ga = gam4[c0 / 4 + g], be = bet4[c0 / 4 + g];
+                        v[4 * g] = (v[4 * g] - mean) * rstd * ga.x + be.x;
+                        v[4 * g + 1] = (v[4 * g + 1] - mean) * rstd * ga.y + be.y;
+                        v[4 * g + 2] = (v[4 * g + 2] - mean) * rstd * ga.z + be.z;
+                        v[4 * g + 3] = (v[4 * g + 3] - mean) * rstd * ga.w + be.w;
+                    }
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (drop) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t bits = dropout_bits(p.seed, (uint64_t)row * (uint64_t)H + (uint64_t)(c0 + j));
+                        v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
+                    }
+                }
+                if (p.rowdot_out) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 w = rdw4[c0 / 4 + g];
+                        dot = fmaf(v[4 * g], w.x, dot);
+                        dot = fmaf(v[4 * g + 1], w.y, dot);
+                        dot = fmaf(v[4 * g + 2], w.z, dot);
+                        dot = fmaf(v[4 * g + 3], w.w, dot);
+                    }
+                }
+                if (p.residual) {
+                    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rbox + box_off(r_in_tile, h * 8 + g));
+                            v[4 * g] += r4.x; v[4 * g + 1] += r4.y; v[4 * g + 2] += r4.z; v[4 * g + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            Vec16<T> u;
+                            u.v = *reinterpret_cast<const uint4*>(rbox + box_off(r_in_tile, h * 4 + g));
+                            float f[8];
+                            u.to_float(f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[8 * g + i] += f[i];
+                        }
+                    }
+                }
+                if (p.out) stage_row(box, h * 32, v);
+            }
+            if (p.out) release_box(&maps.out, box, ob * EPC);
+        }
+        if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
+        if (et == 0) tma_store_wait_read<0>();  // smem must outlive the bulk stores' reads
+    }
+
+    fence_tc_before();
+    __syncthreads();
+    if (warp == 2) {
+        fence_tc_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ---- weight preparation: (optional transpose) + TF32 hi/lo split, or plain copy/transpose for bf16 ----
+template <typename T>
+__global__ void k_prep_weight(const T* __restrict__ w, int rows, int cols, int transpose, int split, T* __restrict__ hi,
+                              T* __restrict__ lo) {
+    const int64_t n = (int64_t)rows * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        // output index i over [orow, ocol] where out = transpose ? w^T : w
+        const int ocols = transpose ? rows : cols;
+        const int64_t orow = i / ocols, ocol = i % ocols;
+        const T val = transpose ? w[ocol * cols + orow] : w[i];
+        if constexpr (sizeof(T) == 4) {
+            if (split) {
+                const float h = __uint_as_float(rna_tf32(val));
+                hi[i] = h;
+                lo[i] = __uint_as_float(rna_tf32(val - h));
+            } else {
+                hi[i] = val;
+            }
+        } else {
+            hi[i] = val;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2D row-major [rows, cols] tensor, box = [box_rows x 128 bytes], SWIZZLE_128B
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int elt, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return 1;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * elt};
+    cuuint32_t box[2] = {(cuuint32_t)(kChunkBytes / elt), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                     gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld elt=%d box_rows=%d)", (int)r, (long long)rows,
+                  (long long)cols, elt, box_rows);
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace tc
+
+// Called by dfw_linear_fwd / dfw_linear_bwd_input.  Returns -1 if the shape is not eligible for the
+// tensor-core path (caller falls back to the SIMT kernel), 0 on success, >0 on error.
+size_t linear_tc_ws_bytes(int64_t Hout, int64_t k1, int64_t k2, int dtype) {
+    const size_t e = dtype == DFW_F32 ? 4 : 2;
+    const size_t per = align_up((size_t)Hout * (size_t)(k1 > 0 ? k1 : 0) * e, 1024) + align_up((size_t)Hout * (size_t)(k2 > 0 ? k2 : 0) * e, 1024);
+    return 2 * per + 1024;
+}
+
+bool linear_tc_eligible(int64_t N, int64_t Hout, int64_t k1, int64_t k2, int dtype, const void* a1, const void* a2) {
+    const int e = dtype == DFW_F32 ? 4 : 2;
+    if (N < 1 || Hout < 16 || Hout > 256 || Hout % 16 || (Hout * e) % 128) return false;
+    if (k1 < 1 || (k1 * e) % 16 || (a2 && (k2 < 1 || (k2 * e) % 16))) return false;
+    if (!aligned16(a1) || (a2 && !aligned16(a2))) return false;
+    if (N >= (1LL << 31)) return false;
+    return true;
+}
+
+// w1/w2 are given in [Hout, k] layout (transpose_w = 0) or [k, Hout] layout to be transposed (transpose_w = 1,
+// used by the input-gradient contraction where the reduction runs over the weight's FIRST index).
+int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2, const void* w2, int64_t k2, int transpose_w,
+                     tc::Args args, int dtype, void* ws, size_t ws_bytes, cudaStream_t s) {
+    using namespace tc;
+    const bool tf32 = dtype == DFW_F32;
+    const int e = tf32 ? 4 : 2;
+    const int64_t Hout = args.Hout;
+    if (ws_bytes < linear_tc_ws_bytes(Hout, k1, a2 ? k2 : 0, dtype)) {
+        set_error("linear_tc: workspace too small");
+        return 1;
+    }
+    // carve the prepared-weight workspace
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+    const size_t sz1 = align_up((size_t)Hout * k1 * e, 1024), sz2 = a2 ? align_up((size_t)Hout * k2 * e, 1024) : 0;
+    void* hi[2] = {base, base + sz1};
+    void* lo[2] = {base + sz1 + sz2, base + 2 * sz1 + sz2};
+    const void* wsrc[2] = {w1, w2};
+    const int64_t ks[2] = {k1, a2 ? k2 : 0};
+    const void* wuse[2] = {w1, w2};
+    for (int i = 0; i < (a2 ? 2 : 1); ++i) {
+        const bool need_prep = tf32 || transpose_w;
+        if (!need_prep) continue;
+        const int rows = transpose_w ? (int)ks[i] : (int)Hout, cols = transpose_w ? (int)Hout : (int)ks[i];
+        const int64_t n = (int64_t)rows * cols;
+        const int blocks = (int)std::min<int64_t>((n + 255) / 256, kNumSMs * 4);
+        if (tf32)
+            k_prep_weight<float><<<blocks, 256, 0, s>>>((const float*)wsrc[i], rows, cols, transpose_w, 1, (float*)hi[i], (float*)lo[i]);
+        else
+            k_prep_weight<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)wsrc[i], rows, cols, transpose_w, 0,
+                                                              (__nv_bfloat16*)hi[i], (__nv_bfloat16*)lo[i]);
+        DFW_LAUNCH_CHECK();
+        wuse[i] = hi[i];
+    }
+
+    Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    args.Npad = (int)((Hout + 15) / 16 * 16);
+    int cols = 32;
+    while (cols < args.Npad) cols <<= 1;
+    args.tmem_cols = cols;
+    const void* as[2] = {a1, a2};
+    for (int i = 0; i < (a2 ? 2 : 1); ++i) {
+        if (make_map(&maps.a[i], as[i], args.N, ks[i], e, kTileM)) return 1;
+        if (make_map(&maps.w_hi[i], wuse[i], Hout, ks[i], e, args.Npad)) return 1;
+        if (tf32 && make_map(&maps.w_lo[i], lo[i], Hout, ks[i], e, args.Npad)) return 1;
+        args.chunks[i] = (int)((ks[i] * e + kChunkBytes - 1) / kChunkBytes);
+    }
+    if (!a2) args.chunks[1] = 0;
+    if (args.out && make_map(&maps.out, args.out, args.N, Hout, e, kTileM)) return 1;
+    if (args.pre_out && make_map(&maps.pre, args.pre_out, args.N, Hout, e, kTileM)) return 1;
+    if (args.residual && make_map(&maps.res, args.residual, args.N, Hout, e, kTileM)) return 1;
+    const int out_boxes = (int)(Hout * e / kChunkBytes);
+
+    // stages: as many as fit; prefer <= ~110 KB so that two CTAs share an SM (epilogue of one overlaps the mainloop of the other)
+    const int total_chunks = args.chunks[0] + args.chunks[1];
+    // the epilogue aliases the pipeline: it needs room for the residual tile plus >= 1 staging box
+    auto fits = [&](int st, size_t budget) {
+        Smem L = carve(tf32, args.Npad, st, out_boxes);
+        return L.total + 1024 <= budget && L.nbuf >= 1;
+    };
+    int stages = kMaxStages;
+    while (stages > 2 && !fits(stages, 110 * 1024)) --stages;
+    if (!fits(stages, 110 * 1024)) {
+        stages = kMaxStages;
+        while (stages > 2 && !fits(stages, 225 * 1024)) --stages;
+    }
+    if (!fits(stages, 225 * 1024)) {
+        set_error("linear_tc: no shared-memory configuration for Hout=%lld", (long long)Hout);
+        return 1;
+    }
+    // not more stages than K chunks, but keep enough bytes for the epilogue aliases
+    while (stages > 2 && stages > total_chunks && fits(stages - 1, 225 * 1024)) --stages;
+    args.stages = stages;
+    const size_t smem = carve(tf32, args.Npad, stages, out_boxes).total + 1024;
+    const unsigned grid = (unsigned)((args.N + kTileM - 1) / kTileM);
+    if (tf32) {
+        auto kern = k_linear_tc<float, true>;
+        DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, s>>>(maps, args);
+    } else {
+        auto kern = k_linear_tc<__nv_bfloat16, false>;
+        DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, s>>>(maps, args);
+    }
+    DFW_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dfw

@@ -243,13 +243,15 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=Fals
     nbytes = N * (k1 + k2) * es + (N * Hout * es if (residual is not None and residual is not a2) else 0) \
         + N * Hout * es * (int(want_out) + int(save_pre)) + (8 * N if stats is not None else 0) + (4 * N if rowdot is not None else 0) \
         + Hout * (k1 + k2) * es
+    ws_bytes = lib.dfw_linear_ws_bytes(Hout, k1, k2, _dt(a1))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev), _prof("linear_fwd", nbytes, 2 * N * Hout * (k1 + k2)):
         check(lib.dfw_linear_fwd(
             a1.data_ptr(), w1.data_ptr(), k1, _ptr(a2), _ptr(w2), 0 if a2 is None else a2.shape[1], _ptr(bias),
             _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(eps), _ptr(residual),
             float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), _ptr(pre), _ptr(stats),
             _ptr(rowdot[0]) if rowdot is not None else None, _ptr(rowdot[1]) if rowdot is not None else None, _ptr(rd_out),
-            N, Hout, flags, _dt(a1), _stream(a1)))
+            N, Hout, flags, _dt(a1), ws.data_ptr(), ws_bytes, _stream(a1)))
     LAUNCH_COUNTER["kernels"] += 1
     return out, pre, stats, rd_out
 
@@ -285,9 +287,11 @@ def linear_bwd_input(g_y, w, row_scale=None, addend=None):
     K = w.shape[1]
     g_a = torch.empty(N, K, dtype=g_y.dtype, device=g_y.device)
     nbytes = (N * Hout + N * K * (1 + int(addend is not None)) + Hout * K) * _esz(g_y)
+    ws_bytes = lib.dfw_linear_ws_bytes(K, Hout, 0, _dt(g_y))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g_y.device)
     with torch.cuda.device(g_y.device), _prof("linear_bwd_input", nbytes, 2 * N * Hout * K):
         check(lib.dfw_linear_bwd_input(g_y.data_ptr(), w.data_ptr(), _ptr(row_scale), _ptr(addend), g_a.data_ptr(), N, Hout, K,
-                                       _dt(g_y), _stream(g_y)))
+                                       _dt(g_y), ws.data_ptr(), ws_bytes, _stream(g_y)))
     LAUNCH_COUNTER["kernels"] += 1
     return g_a
 

@@ -85,13 +85,18 @@ int dfw_sage_aggregate(const int32_t* rowptr, const int32_t* col, const float* r
  *     and `out` may then be NULL.  Dropout keep-mask is a pure function of
  *     (seed, row*Hout+col): the backward regenerates it.
  * ---------------------------------------------------------------------------------------- */
+/*     Tensor-core path (tcgen05/TMEM/TMA; bf16 kind::f16, fp32 as error-compensated 3xTF32) is taken when
+ *     16 <= Hout <= 256, Hout % 16 == 0, k*sizeof(dtype) % 16 == 0 and `ws` holds dfw_linear_ws_bytes();
+ *     other shapes (e.g. the encoder's K = 10) run the exact-fp32 SIMT kernel.  ws may be NULL (SIMT). */
+size_t dfw_linear_ws_bytes(int64_t Hout, int64_t k1, int64_t k2, int dtype);
 int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1,
                    const void* a2, const void* w2, int64_t k2,
                    const float* bias, const float* ln_gamma, const float* ln_beta, float ln_eps,
                    const void* residual, float dropout_p, uint64_t seed,
                    void* out, void* pre_out, float* ln_stats,
                    const float* rowdot_w, const float* rowdot_b, float* rowdot_out,
-                   int64_t N, int64_t Hout, int flags, int dtype, dfw_stream_t stream);
+                   int64_t N, int64_t Hout, int flags, int dtype,
+                   void* ws, size_t ws_bytes, dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (d1) backward of the epilogue of (c): given g_out = dL/d out, produce g_y = dL/d y.
@@ -117,7 +122,9 @@ int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const float* rowd
  *      w = lin_r.weight with addend = the residual-path gradient.
  * ---------------------------------------------------------------------------------------- */
 int dfw_linear_bwd_input(const void* g_y, const void* w, const float* row_scale, const void* addend,
-                         void* g_a, int64_t N, int64_t Hout, int64_t K, int dtype, dfw_stream_t stream);
+                         void* g_a, int64_t N, int64_t Hout, int64_t K, int dtype,
+                         void* ws /* dfw_linear_ws_bytes(K, Hout, 0, dtype), nullable */, size_t ws_bytes,
+                         dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (d3) weight gradients of (c):  dW1 = g_y^T . a1  [Hout,k1], dW2 = g_y^T . a2 [Hout,k2],

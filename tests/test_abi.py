@@ -40,7 +40,7 @@ def test_size_queries_and_argument_errors_need_no_gpu():
     assert rc != 0 and b"negative" in lib.dfw_last_error()
     with pytest.raises(_cabi.DfwError):
         _cabi.check(lib.dfw_linear_fwd(None, None, 0, None, None, 0, None, None, None, 1e-5, None, 0.0, 0, None, None, None,
-                                       None, None, None, 4, 512, 0, 0, None))
+                                       None, None, None, 4, 512, 0, 0, None, 0, None))
 
 
 def test_product_path_refuses_cpu_tensors():
