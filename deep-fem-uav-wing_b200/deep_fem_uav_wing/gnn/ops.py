@@ -212,7 +212,7 @@ def aggregate(rowptr, col, row_scale, x, addend=None):
     amin = (2 + (addend is not None)) * N * H * _esz(x) + 4 * E + 4 * (N + 1)
     with torch.cuda.device(x.device), _prof("aggregate", amin):
         check(lib.dfw_sage_aggregate(rowptr.data_ptr(), col.data_ptr(), _ptr(row_scale), x.data_ptr(),
-                                     _ptr(addend.contiguous() if addend is not None else None), out.data_ptr(), N, H, _dt(x),
+                                     _ptr(addend.contiguous() if addend is not None else None), out.data_ptr(), N, E, H, _dt(x),
                                      _stream(x)))
     LAUNCH_COUNTER["kernels"] += 1
     return out

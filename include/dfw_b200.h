@@ -69,7 +69,7 @@ int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src,
  * ---------------------------------------------------------------------------------------- */
 int dfw_sage_aggregate(const int32_t* rowptr, const int32_t* col, const float* row_scale,
                        const void* x, const void* addend, void* out,
-                       int64_t N, int64_t H, int dtype, dfw_stream_t stream);
+                       int64_t N, int64_t E, int64_t H, int dtype, dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (c) fused node-wise linear:

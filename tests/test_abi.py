@@ -34,7 +34,7 @@ def test_size_queries_and_argument_errors_need_no_gpu():
     assert lib.dfw_linear_bwd_weight_ws_bytes(1000, 128, 128, 128) > 0
     assert lib.dfw_epilogue_bwd_ws_bytes(1000, 128) > 0
     # argument validation happens before any CUDA call
-    rc = lib.dfw_sage_aggregate(None, None, None, None, None, None, 10, 3, 0, None)
+    rc = lib.dfw_sage_aggregate(None, None, None, None, None, None, 10, 5, 3, 0, None)
     assert rc != 0 and b"multiple of 16" in lib.dfw_last_error()
     rc = lib.dfw_csr_build(None, -1, 5, 0, None, None, None, None, None, None, 0, None)
     assert rc != 0 and b"negative" in lib.dfw_last_error()
