@@ -593,13 +593,35 @@ DwPlan dw_plan(int64_t N, int64_t Hout, int64_t k1, int64_t k2) {
     p.db_bytes = align_up(sizeof(float) * (size_t)splits * p.tiles_i * DW_BM, 256);
     return p;
 }
+// tensor-core variant: one CTA per [128 x 128] tile and node slice, ~one CTA per SM in total
+DwPlan dw_plan_tc(int64_t N, int64_t Hout, int64_t k1, int64_t k2) {
+    DwPlan p;
+    p.tiles_i = (int)(Hout / 128);
+    p.tiles_j1 = (int)(k1 / 128);
+    p.tiles_j2 = (int)(k2 / 128);
+    const int tiles = std::max(1, p.tiles_i * (p.tiles_j1 + p.tiles_j2));
+    int64_t splits = std::max<int64_t>(1, kNumSMs / tiles);
+    int64_t per = (N + splits - 1) / splits;
+    per = std::max<int64_t>(32, (per + 31) / 32 * 32);
+    splits = std::max<int64_t>(1, (N + per - 1) / per);
+    p.splits = (int)splits;
+    p.nodes_per_split = per;
+    p.part_bytes = align_up(sizeof(float) * (size_t)splits * tiles * 128 * 128, 256);
+    p.db_bytes = colsum_ws_bytes(Hout);
+    return p;
+}
 }  // namespace
 }  // namespace dfw
 
 extern "C" size_t dfw_linear_bwd_weight_ws_bytes(int64_t N, int64_t Hout, int64_t k1, int64_t k2) {
     if (N < 0 || Hout < 1 || k1 < 1 || k2 < 0) return 0;
     dfw::DwPlan p = dfw::dw_plan(N, Hout, k1, k2);
-    return p.part_bytes + p.db_bytes;
+    size_t need = p.part_bytes + p.db_bytes;
+    if (Hout % 128 == 0 && k1 % 128 == 0 && k2 % 128 == 0) {
+        dfw::DwPlan t = dfw::dw_plan_tc(N, Hout, k1, k2);
+        need = std::max(need, t.part_bytes + t.db_bytes);
+    }
+    return need;
 }
 
 extern "C" int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1, const void* a2, int64_t k2,
@@ -611,10 +633,26 @@ extern "C" int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1
     DFW_REQUIRE(g_y && a1 && dw1, "dfw_linear_bwd_weight: null pointer");
     DFW_REQUIRE((a2 == nullptr) == (dw2 == nullptr), "dfw_linear_bwd_weight: a2 and dw2 go together");
     if (!a2) k2 = 0;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (N > 0 && !force_simt() && dw_tc_eligible(N, Hout, k1, k2, dtype, g_y, a1, a2)) {
+        DwPlan pt = dw_plan_tc(N, Hout, k1, k2);
+        DFW_REQUIRE(ws && ws_bytes >= pt.part_bytes + pt.db_bytes, "dfw_linear_bwd_weight: workspace too small (%zu < %zu)",
+                    ws_bytes, pt.part_bytes + pt.db_bytes);
+        float* part = reinterpret_cast<float*>(ws);
+        float* part_db = dbias ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pt.part_bytes) : nullptr;
+        int rc = dw_tc_launch(g_y, a1, k1, a2, k2, N, Hout, dtype, part, pt.splits, pt.nodes_per_split, s);
+        if (rc) return rc;
+        if (dbias && (rc = colsum_launch(g_y, N, Hout, dtype, part_db, dbias, accumulate, s))) return rc;
+        const int64_t total = Hout * (k1 + k2);
+        const int rgrid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 8);
+        k_dw_reduce<128, 128><<<rgrid, 256, 0, s>>>(part, nullptr, pt.splits, pt.tiles_i, pt.tiles_j1, pt.tiles_j2, Hout, k1, k2, dw1,
+                                                    dw2, nullptr, accumulate);
+        DFW_LAUNCH_CHECK();
+        return 0;
+    }
     DwPlan pl = dw_plan(N, Hout, k1, k2);
     DFW_REQUIRE(ws && ws_bytes >= pl.part_bytes + pl.db_bytes, "dfw_linear_bwd_weight: workspace too small (%zu < %zu)",
                 ws_bytes, pl.part_bytes + pl.db_bytes);
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     LinArgs a{};
     a.a1 = g_y; a.w1 = a1; a.w2 = a2; a.k1 = k1; a.k2 = k2; a.N = N; a.Hout = Hout;
     a.part = reinterpret_cast<float*>(ws);

@@ -28,13 +28,13 @@
 
 #include "dfw_common.cuh"
 #include "dfw_linear_tc.cuh"
+#include "dfw_tc_common.cuh"
 
 namespace dfw {
 namespace tc {
 
 constexpr int kThreads = 192;
 constexpr int kTileM = 128;
-constexpr int kChunkBytes = 128;  // one SWIZZLE_128B atom row
 constexpr int kMaxStages = 6;
 
 struct Maps {
@@ -44,116 +44,6 @@ struct Maps {
     CUtensorMap out, pre, res;  // [N, Hout] tensors of the epilogue, boxes of [128 rows x 128 B]
 };
 
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok;
-    uint32_t spins = 0;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (!ok && ++spins > (1u << 24)) {  // a legitimate wait lasts microseconds: this is a protocol bug, fail loudly
-            printf("dfw_linear_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
-            __trap();
-        }
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows x 128 B = 1024 B)
-// | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-
-template <bool TF32>
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (TF32) {
-        asm volatile(
-            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
-        "[%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void fence_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps only
-
-// One [128 rows x 128 B] box in SWIZZLE_128B layout: 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4).
-// A thread that owns row r touches 8 distinct bank groups per quarter-warp: conflict-free.
-__device__ __forceinline__ uint32_t box_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 // smem carve-up (all offsets from a 1024-aligned base)
 struct Smem {
@@ -274,6 +164,11 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             uint32_t accumulate = 0;
+            // fp32: hi*hi products alternate between `nacc` accumulators, all cross terms go to one more
+            // (see tmem_combine); bf16: a single accumulator
+            uint32_t acc_main[2] = {0u, 0u}, acc_cross = 0u;
+            const uint32_t t_cross = tmem_base + (uint32_t)(p.nacc * p.Npad);
+            int kstep = 0;
             for (int c = 0; c < total_chunks; ++c) {
                 mbar_wait(TF32 ? &conv[stage] : &full[stage], phase);
                 fence_tc_after();
@@ -285,9 +180,13 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                     if (TF32) {
                         const uint64_t a_lo = make_desc(st + L.a_lo + k * 32);
                         const uint64_t w_lo = make_desc(st + L.w_lo + k * 32);
-                        umma<TF32>(tmem_base, a_lo, w_hi, idesc, accumulate);
-                        umma<TF32>(tmem_base, a_hi, w_lo, idesc, 1u);
-                        umma<TF32>(tmem_base, a_hi, w_hi, idesc, 1u);
+                        const int m = kstep % p.nacc;
+                        umma<TF32>(t_cross, a_lo, w_hi, idesc, acc_cross);
+                        umma<TF32>(t_cross, a_hi, w_lo, idesc, 1u);
+                        umma<TF32>(tmem_base + (uint32_t)(m * p.Npad), a_hi, w_hi, idesc, acc_main[m]);
+                        acc_cross = 1u;
+                        acc_main[m] = 1u;
+                        ++kstep;
                     } else {
                         umma<TF32>(tmem_base, a_hi, w_hi, idesc, accumulate);
                     }
@@ -335,6 +234,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         const bool rok = row < p.N;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const int H = p.Hout;
+        if (TF32) tmem_combine(t_row, H, p.nacc + 1, p.Npad);
         const int n32 = H / 32;
         const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
         const bool ln = p.flags & DFW_EP_LAYERNORM;
@@ -551,7 +451,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D row-major [rows, cols] tensor, box = [box_rows x 128 bytes], SWIZZLE_128B
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int elt, int box_rows) {
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int elt, int box_rows, bool atom32b) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -562,7 +462,8 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
     cuuint32_t box[2] = {(cuuint32_t)(kChunkBytes / elt), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
-                     gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld elt=%d box_rows=%d)", (int)r, (long long)rows,
@@ -629,8 +530,10 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
     Maps maps;
     memset(&maps, 0, sizeof(maps));
     args.Npad = (int)((Hout + 15) / 16 * 16);
+    args.nacc = (tf32 && 3 * args.Npad <= 512) ? 2 : 1;
+    const int acc_cols = tf32 ? (args.nacc + 1) * args.Npad : args.Npad;
     int cols = 32;
-    while (cols < args.Npad) cols <<= 1;
+    while (cols < acc_cols) cols <<= 1;
     args.tmem_cols = cols;
     const void* as[2] = {a1, a2};
     for (int i = 0; i < (a2 ? 2 : 1); ++i) {

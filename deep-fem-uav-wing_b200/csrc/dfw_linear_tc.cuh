@@ -11,6 +11,7 @@ struct Args {
     int Hout;        // logical output width
     int Npad;        // UMMA N (multiple of 16)
     int tmem_cols;   // power of two >= 32
+    int nacc;        // fp32: number of hi*hi accumulators (cross terms use one more)
     int chunks[2];   // 128-byte K chunks per operand pair
     int stages;
     int flags;
@@ -25,4 +26,9 @@ size_t linear_tc_ws_bytes(int64_t Hout, int64_t k1, int64_t k2, int dtype);
 bool linear_tc_eligible(int64_t N, int64_t Hout, int64_t k1, int64_t k2, int dtype, const void* a1, const void* a2);
 int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2, const void* w2, int64_t k2, int transpose_w,
                      tc::Args args, int dtype, void* ws, size_t ws_bytes, cudaStream_t s);
+bool dw_tc_eligible(int64_t N, int64_t Hout, int64_t k1, int64_t k2, int dtype, const void* g, const void* a1, const void* a2);
+int dw_tc_launch(const void* g_y, const void* a1, int64_t k1, const void* a2, int64_t k2, int64_t N, int64_t Hout, int dtype,
+                 float* part, int splits, int64_t nodes_per_split, cudaStream_t s);
+size_t colsum_ws_bytes(int64_t H);
+int colsum_launch(const void* g_y, int64_t N, int64_t H, int dtype, float* part, float* dbias, int accumulate, cudaStream_t s);
 }  // namespace dfw
