@@ -287,9 +287,9 @@ int dw_tc_launch(const void* g_y, const void* a1, int64_t k1, const void* a2, in
     const int e = tf32 ? 4 : 2;
     DwMaps maps;
     memset(&maps, 0, sizeof(maps));
-    if (make_map(&maps.g, g_y, N, Hout, e, kDwNodes, tf32)) return 1;
-    if (make_map(&maps.a[0], a1, N, k1, e, kDwNodes, tf32)) return 1;
-    if (a2 && make_map(&maps.a[1], a2, N, k2, e, kDwNodes, tf32)) return 1;
+    if (make_map(&maps.g, g_y, N, Hout, e, kDwNodes, tf32 ? kMapSw128Atom32 : kMapSw128)) return 1;
+    if (make_map(&maps.a[0], a1, N, k1, e, kDwNodes, tf32 ? kMapSw128Atom32 : kMapSw128)) return 1;
+    if (a2 && make_map(&maps.a[1], a2, N, k2, e, kDwNodes, tf32 ? kMapSw128Atom32 : kMapSw128)) return 1;
     DwArgs p{};
     p.N = N;
     p.nodes_per_split = nodes_per_split;

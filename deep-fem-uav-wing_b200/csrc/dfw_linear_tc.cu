@@ -53,8 +53,10 @@ struct Smem {
 };
 __host__ __device__ inline Smem carve(bool tf32, int Npad, int stages, int out_boxes) {
     Smem s;
-    const uint32_t a = kTileM * kChunkBytes;                                  // 16 KB
-    const uint32_t w = ((uint32_t)Npad * kChunkBytes + 1023u) / 1024u * 1024u;  // Npad rows x 128 B
+    const uint32_t cb = tf32 ? 64u : 128u;                      // K bytes per pipeline stage (see kernel)
+    const uint32_t a = kTileM * cb;                             // activation tile: 8 KB (fp32) / 16 KB (bf16)
+    const uint32_t w = ((uint32_t)Npad * cb + 1023u) / 1024u * 1024u;
+    const uint32_t box = kTileM * kChunkBytes;                  // epilogue boxes stay [128 rows x 128 B]
     s.a_hi = 0;
     s.a_lo = a;
     s.w_hi = tf32 ? 2 * a : a;
@@ -62,8 +64,8 @@ __host__ __device__ inline Smem carve(bool tf32, int Npad, int stages, int out_b
     s.stage_bytes = tf32 ? 2 * a + 2 * w : a + w;
     const uint32_t pipe = s.stage_bytes * stages;
     s.res = 0;
-    s.staging = (uint32_t)out_boxes * a;
-    const uint32_t left = pipe > s.staging ? (pipe - s.staging) / a : 0;
+    s.staging = (uint32_t)out_boxes * box;
+    const uint32_t left = pipe > s.staging ? (pipe - s.staging) / box : 0;
     s.nbuf = left > 4 ? 4 : left;
     s.cvec = pipe;
     s.bars = s.cvec + 4 * 256 * 4;
@@ -73,7 +75,13 @@ __host__ __device__ inline Smem carve(bool tf32, int Npad, int stages, int out_b
 
 template <typename T, bool TF32>
 __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ Maps maps, const Args p) {
-    constexpr int EPC = kChunkBytes / (int)sizeof(T);  // elements (columns) per 128-byte box: 32 fp32 / 64 bf16
+    constexpr int EPC = kChunkBytes / (int)sizeof(T);  // elements (columns) per 128-byte epilogue box: 32 fp32 / 64 bf16
+    // Main-loop K chunk: 128 B (SWIZZLE_128B) for bf16, 64 B (SWIZZLE_64B) for fp32.  The fp32 stage holds four
+    // tiles (a_hi, a_lo, w_hi, w_lo); with 64-byte chunks a stage is 32 KB, three stages fit in < 110 KB and TWO
+    // CTAs share an SM, so the epilogue of one tile overlaps the main loop of another (one CTA per SM leaves the
+    // epilogue latency - ~7 us per tile - fully exposed; measured with the clock probes of tools/tc_timeline.py).
+    constexpr int CB = TF32 ? 64 : 128;
+    constexpr int KPC = CB / (int)sizeof(T);           // K elements per chunk
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int out_boxes = p.Hout / EPC;
@@ -132,12 +140,12 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t stage_tx = (uint32_t)(kTileM * kChunkBytes + p.Npad * kChunkBytes * (TF32 ? 2 : 1));
+            const uint32_t stage_tx = (uint32_t)(kTileM * CB + p.Npad * CB * (TF32 ? 2 : 1));
             int stage = 0;
             uint32_t phase = 0;
             for (int c = 0; c < total_chunks; ++c) {
                 const int seg = c >= p.chunks[0];
-                const int kc = (seg ? c - p.chunks[0] : c) * EPC;
+                const int kc = (seg ? c - p.chunks[0] : c) * KPC;
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* st = smem + (size_t)stage * L.stage_bytes;
                 mbar_arrive_expect_tx(&full[stage], stage_tx);
@@ -168,18 +176,19 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             // (see tmem_combine); bf16: a single accumulator
             uint32_t acc_main[2] = {0u, 0u}, acc_cross = 0u;
             const uint32_t t_cross = tmem_base + (uint32_t)(p.nacc * p.Npad);
+            const uint64_t dbase = make_desc_k<CB>(0);  // every field but the 14-bit start address
             int kstep = 0;
             for (int c = 0; c < total_chunks; ++c) {
                 mbar_wait(TF32 ? &conv[stage] : &full[stage], phase);
                 fence_tc_after();
                 const uint32_t st = smem_u32(smem + (size_t)stage * L.stage_bytes);
 #pragma unroll
-                for (int k = 0; k < kChunkBytes / 32; ++k) {  // UMMA_K = 32 bytes (16 bf16 / 8 tf32)
-                    const uint64_t a_hi = make_desc(st + L.a_hi + k * 32);
-                    const uint64_t w_hi = make_desc(st + L.w_hi + k * 32);
+                for (int k = 0; k < CB / 32; ++k) {  // UMMA_K = 32 bytes (16 bf16 / 8 tf32); +32 B = +2 in the address field
+                    const uint64_t a_hi = dbase + ((st + L.a_hi + k * 32) >> 4);
+                    const uint64_t w_hi = dbase + ((st + L.w_hi + k * 32) >> 4);
                     if (TF32) {
-                        const uint64_t a_lo = make_desc(st + L.a_lo + k * 32);
-                        const uint64_t w_lo = make_desc(st + L.w_lo + k * 32);
+                        const uint64_t a_lo = dbase + ((st + L.a_lo + k * 32) >> 4);
+                        const uint64_t w_lo = dbase + ((st + L.w_lo + k * 32) >> 4);
                         const int m = kstep % p.nacc;
                         umma<TF32>(t_cross, a_lo, w_hi, idesc, acc_cross);
                         umma<TF32>(t_cross, a_hi, w_lo, idesc, 1u);
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 float4* hi = reinterpret_cast<float4*>(st + L.a_hi);
                 float4* lo = reinterpret_cast<float4*>(st + L.a_lo);
 #pragma unroll
-                for (int i = 0; i < (kTileM * kChunkBytes / 16) / 128; ++i) {  // position-preserving: swizzle-agnostic
+                for (int i = 0; i < (kTileM * CB / 16) / 128; ++i) {  // position-preserving: swizzle-agnostic
                     const int idx = et + i * 128;
                     const float4 a = hi[idx];
                     float4 h, l;
@@ -451,7 +460,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D row-major [rows, cols] tensor, box = [box_rows x 128 bytes], SWIZZLE_128B
-int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int elt, int box_rows, bool atom32b) {
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int elt, int box_rows, int mode) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -459,11 +468,13 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int e
     }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)cols * elt};
-    cuuint32_t box[2] = {(cuuint32_t)(kChunkBytes / elt), (cuuint32_t)box_rows};
+    const int inner_bytes = mode == kMapSw64 ? 64 : kChunkBytes;
+    cuuint32_t box[2] = {(cuuint32_t)(inner_bytes / elt), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
                      gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     mode == kMapSw128Atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (mode == kMapSw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld elt=%d box_rows=%d)", (int)r, (long long)rows,
@@ -530,17 +541,21 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
     Maps maps;
     memset(&maps, 0, sizeof(maps));
     args.Npad = (int)((Hout + 15) / 16 * 16);
-    args.nacc = (tf32 && 3 * args.Npad <= 512) ? 2 : 1;
+    // one hi*hi accumulator + one cross accumulator when that keeps TMEM <= 256 columns (two CTAs per SM);
+    // two hi*hi accumulators otherwise if they fit (halves the truncation bias, see tmem_combine)
+    args.nacc = !tf32 ? 1 : (2 * args.Npad <= 256 ? 1 : (3 * args.Npad <= 512 ? 2 : 1));
     const int acc_cols = tf32 ? (args.nacc + 1) * args.Npad : args.Npad;
     int cols = 32;
     while (cols < acc_cols) cols <<= 1;
     args.tmem_cols = cols;
     const void* as[2] = {a1, a2};
     for (int i = 0; i < (a2 ? 2 : 1); ++i) {
-        if (make_map(&maps.a[i], as[i], args.N, ks[i], e, kTileM)) return 1;
-        if (make_map(&maps.w_hi[i], wuse[i], Hout, ks[i], e, args.Npad)) return 1;
-        if (tf32 && make_map(&maps.w_lo[i], lo[i], Hout, ks[i], e, args.Npad)) return 1;
-        args.chunks[i] = (int)((ks[i] * e + kChunkBytes - 1) / kChunkBytes);
+        const int mm = tf32 ? kMapSw64 : kMapSw128;  // main-loop chunk: 64 B for fp32, 128 B for bf16
+        const int cb = tf32 ? 64 : 128;
+        if (make_map(&maps.a[i], as[i], args.N, ks[i], e, kTileM, mm)) return 1;
+        if (make_map(&maps.w_hi[i], wuse[i], Hout, ks[i], e, args.Npad, mm)) return 1;
+        if (tf32 && make_map(&maps.w_lo[i], lo[i], Hout, ks[i], e, args.Npad, mm)) return 1;
+        args.chunks[i] = (int)((ks[i] * e + cb - 1) / cb);
     }
     if (!a2) args.chunks[1] = 0;
     if (args.out && make_map(&maps.out, args.out, args.N, Hout, e, kTileM)) return 1;

@@ -54,6 +54,13 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows x 128 B = 1024 B)
 // | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+// K-major descriptor for a tile whose rows are CBYTES bytes (= the swizzle span): 128 -> SWIZZLE_128B (layout 2,
+// 8 rows = 1024 B), 64 -> SWIZZLE_64B (layout 4, 8 rows = 512 B)
+template <int CBYTES>
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
+    constexpr uint64_t sbo = CBYTES * 8, layout = CBYTES == 128 ? 2 : 4;
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((sbo >> 4) << 32) | ((uint64_t)1 << 46) | (layout << 61);
+}
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
@@ -153,7 +160,8 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 __device__ __forceinline__ uint32_t box_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 
-int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int elt, int box_rows, bool atom32b = false);
+enum { kMapSw128 = 0, kMapSw128Atom32 = 1, kMapSw64 = 2 };
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int elt, int box_rows, int mode = kMapSw128);
 
 }  // namespace tc
 }  // namespace dfw
