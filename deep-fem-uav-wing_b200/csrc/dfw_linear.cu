@@ -457,7 +457,19 @@ __global__ void k_dw_reduce(const float* __restrict__ part, const float* __restr
             const int64_t i = e / k, j = e % k;
             const int ti = (int)(i / BM), tj = (int)(j / BN) + (second ? tiles_j1 : 0);
             const int64_t off = (int64_t)(ti * (tiles_j1 + tiles_j2) + tj) * (BM * BN) + (i % BM) * BN + (j % BN);
-            for (int sp = 0; sp < splits; ++sp) s += part[(int64_t)sp * tiles * (BM * BN) + off];
+            {  // four interleaved partial sums (fixed order): keeps 4 loads in flight instead of a dependent chain
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                const int64_t st = (int64_t)tiles * (BM * BN);
+                int sp = 0;
+                for (; sp + 3 < splits; sp += 4) {
+                    q0 += part[(int64_t)sp * st + off];
+                    q1 += part[(int64_t)(sp + 1) * st + off];
+                    q2 += part[(int64_t)(sp + 2) * st + off];
+                    q3 += part[(int64_t)(sp + 3) * st + off];
+                }
+                for (; sp < splits; ++sp) q0 += part[(int64_t)sp * st + off];
+                s = (q0 + q1) + (q2 + q3);
+            }
             dst = (second ? dw2 : dw1) + e;
         } else {
             const int64_t i = idx - n1 - n2;

@@ -262,12 +262,16 @@ __global__ void __launch_bounds__(256) k_colsum_partial(const T* __restrict__ g,
         part[(int64_t)blockIdx.x * H + c] = s;
     }
 }
-__global__ void k_colsum_final(const float* __restrict__ part, int blocks, int H, float* __restrict__ out, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_colsum_final(const float* __restrict__ part, int blocks, int H, float* __restrict__ out,
+                                                       int accumulate) {
+    // one warp per column, lanes stride over the partials, fixed shuffle tree (deterministic)
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= H) return;
     float s = 0.f;
-    for (int b = 0; b < blocks; ++b) s += part[(int64_t)b * H + c];
-    out[c] = accumulate ? out[c] + s : s;
+    for (int b = lane; b < blocks; b += 32) s += part[(int64_t)b * H + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = accumulate ? out[c] + s : s;
 }
 
 }  // namespace tc
@@ -327,7 +331,7 @@ int colsum_launch(const void* g_y, int64_t N, int64_t H, int dtype, float* part,
     if (dtype == DFW_F32) k_colsum_partial<float><<<blocks, 256, 0, s>>>((const float*)g_y, N, (int)H, part);
     else k_colsum_partial<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)g_y, N, (int)H, part);
     DFW_LAUNCH_CHECK();
-    k_colsum_final<<<(unsigned)((H + 127) / 128), 128, 0, s>>>(part, blocks, (int)H, dbias, accumulate);
+    k_colsum_final<<<(unsigned)((H * 32 + 255) / 256), 256, 0, s>>>(part, blocks, (int)H, dbias, accumulate);
     DFW_LAUNCH_CHECK();
     return 0;
 }

@@ -27,7 +27,6 @@ namespace {
 constexpr int kEbThreads = 256;
 constexpr int kEbWarps = kEbThreads / 32;
 constexpr int kEbMaxBlocks = kNumSMs * 4;
-constexpr int kMaxVPL = 2;  // 32 lanes * 4 elements * 2 = 256 columns
 
 template <typename T>
 __device__ __forceinline__ void ld4(const T* p, float* v) {
@@ -56,13 +55,14 @@ struct EbArgs {
     const void* pre_out; const float* ln_stats; const void* act;
     const float* gamma; const float* beta;
     uint32_t drop_thr; float drop_scale; uint64_t seed;
-    void* g_y; float* part;  // [blocks][3][H] : (dgamma | d_rowdot_w), dbeta, (row 2, col 0) = sum g_rowdot
+    void* g_y; float* part;  // [blocks][4][H] : (dgamma | d_rowdot_w), dbeta, (slot 2, col 0) = sum g_rowdot, colsum(g_y)
     int64_t N; int H; int flags;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(kEbThreads) k_epilogue_bwd(const EbArgs p) {
-    __shared__ float red[kEbWarps][2][256 + 1];
+template <typename T, int VPL>
+__global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(const EbArgs p) {
+    constexpr int kMaxVPL = VPL;  // 16-byte column groups per lane: 1 (H <= 128) or 2 (H <= 256)
+    __shared__ float red[kEbWarps][3][256 + 1];
     __shared__ float red_b[kEbWarps];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int H = p.H;
@@ -91,74 +91,102 @@ __global__ void __launch_bounds__(kEbThreads) k_epilogue_bwd(const EbArgs p) {
     }
     float sum_gr = 0.f;
 
+    float c2[kMaxVPL][4];  // column sums of g_y (= bias gradient of the producing linear)
+#pragma unroll
+    for (int v = 0; v < kMaxVPL; ++v)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c2[v][j] = 0.f;
+
+    // kR rows per warp and iteration: all loads of the kR rows are issued before any arithmetic, so a warp
+    // keeps 2*kR 512-byte requests in flight (one row at a time left the kernel latency-bound at 28 % of HBM).
+    constexpr int kR = VPL == 1 ? 4 : 2;
     const int64_t warps = (int64_t)gridDim.x * kEbWarps;
-    for (int64_t row = (int64_t)blockIdx.x * kEbWarps + wid; row < p.N; row += warps) {
-        float g[kMaxVPL][4], xh[kMaxVPL][4];
-        float mean = 0.f, rstd = 1.f;
-        if (ln) {
-            mean = __ldg(p.ln_stats + 2 * row);
-            rstd = __ldg(p.ln_stats + 2 * row + 1);
-        }
-        const float gr = p.g_rowdot ? __ldg(p.g_rowdot + row) : 0.f;
-        if (p.g_rowdot && lane == 0) sum_gr += gr;
-        float s1 = 0.f, s2 = 0.f;
+    for (int64_t row0 = ((int64_t)blockIdx.x * kEbWarps + wid) * kR; row0 < p.N; row0 += warps * kR) {
+        float g[kR][kMaxVPL][4], y[kR][kMaxVPL][4];
+        float mean[kR], rstd[kR], gr[kR];
+        bool rv[kR];
 #pragma unroll
-        for (int v = 0; v < kMaxVPL; ++v) {
-            if (!vok[v]) continue;
-            const int c = (lane + v * 32) * 4;
-            const int64_t off = row * H + c;
-            if (p.g_rowdot) {
+        for (int r = 0; r < kR; ++r) {
+            const int64_t row = row0 + r;
+            rv[r] = row < p.N;
+            mean[r] = 0.f; rstd[r] = 1.f; gr[r] = 0.f;
+            if (rv[r]) {
+                if (ln) {
+                    mean[r] = __ldg(p.ln_stats + 2 * row);
+                    rstd[r] = __ldg(p.ln_stats + 2 * row + 1);
+                }
+                if (p.g_rowdot) gr[r] = __ldg(p.g_rowdot + row);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) g[v][j] = gr * rdw[v][j];
-            } else {
-                ld4(gout + off, g[v]);
+                for (int v = 0; v < kMaxVPL; ++v) {
+                    if (!vok[v]) continue;
+                    const int64_t off = row * H + (lane + v * 32) * 4;
+                    if (!p.g_rowdot) ld4(gout + off, g[r][v]);
+                    if (ln) ld4(pre + off, y[r][v]);
+                    else if (act) ld4(act + off, y[r][v]);
+                }
             }
-            float keep[4] = {1.f, 1.f, 1.f, 1.f};
-            if (drop) {
+        }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    keep[j] = dropout_bits(p.seed, (uint64_t)off + j) >= p.drop_thr ? p.drop_scale : 0.f;
+        for (int r = 0; r < kR; ++r) {
+            if (!rv[r]) continue;  // warp-uniform
+            const int64_t row = row0 + r;
+            if (p.g_rowdot && lane == 0) sum_gr += gr[r];
+            float xh[kMaxVPL][4];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int v = 0; v < kMaxVPL; ++v) {
+                if (!vok[v]) continue;
+                const int64_t off = row * H + (lane + v * 32) * 4;
+                if (p.g_rowdot) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) g[r][v][j] = gr[r] * rdw[v][j];
+                }
+                float keep[4] = {1.f, 1.f, 1.f, 1.f};
+                if (drop) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        keep[j] = dropout_bits(p.seed, (uint64_t)off + j) >= p.drop_thr ? p.drop_scale : 0.f;
+                }
+                if (ln) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        xh[v][j] = (y[r][v][j] - mean[r]) * rstd[r];
+                        const float z = xh[v][j] * gam[v][j] + bet[v][j];
+                        float gg = g[r][v][j] * keep[j];
+                        if (relu && !(z > 0.f)) gg = 0.f;
+                        c0[v][j] += gg * xh[v][j];  // dgamma
+                        c1[v][j] += gg;             // dbeta
+                        gg *= gam[v][j];
+                        g[r][v][j] = gg;
+                        s1 += gg;
+                        s2 += gg * xh[v][j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float a = act ? y[r][v][j] : 1.f;
+                        if (p.g_rowdot) c0[v][j] += gr[r] * (a * keep[j]);  // d_rowdot_w (a is post-ReLU)
+                        float gg = g[r][v][j] * keep[j];
+                        if (relu && !(a > 0.f)) gg = 0.f;
+                        g[r][v][j] = gg;
+                    }
+                }
             }
             if (ln) {
-                float y[4];
-                ld4(pre + off, y);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    xh[v][j] = (y[j] - mean) * rstd;
-                    const float z = xh[v][j] * gam[v][j] + bet[v][j];
-                    float gg = g[v][j] * keep[j];
-                    if (relu && !(z > 0.f)) gg = 0.f;
-                    c0[v][j] += gg * xh[v][j];  // dgamma
-                    c1[v][j] += gg;             // dbeta
-                    gg *= gam[v][j];
-                    g[v][j] = gg;
-                    s1 += gg;
-                    s2 += gg * xh[v][j];
-                }
-            } else {
-                float a[4] = {1.f, 1.f, 1.f, 1.f};
-                if (act) ld4(act + off, a);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (p.g_rowdot) c0[v][j] += gr * (a[j] * keep[j]);  // d_rowdot_w (a is post-ReLU)
-                    float gg = g[v][j] * keep[j];
-                    if (relu && !(a[j] > 0.f)) gg = 0.f;
-                    g[v][j] = gg;
-                }
+                s1 = warp_sum(s1) * invH;
+                s2 = warp_sum(s2) * invH;
             }
-        }
-        if (ln) {
-            s1 = warp_sum(s1) * invH;
-            s2 = warp_sum(s2) * invH;
-        }
 #pragma unroll
-        for (int v = 0; v < kMaxVPL; ++v) {
-            if (!vok[v]) continue;
-            const int c = (lane + v * 32) * 4;
-            float o[4];
+            for (int v = 0; v < kMaxVPL; ++v) {
+                if (!vok[v]) continue;
+                float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = ln ? rstd * (g[v][j] - s1 - xh[v][j] * s2) : g[v][j];
-            st4(gy + row * H + c, o);
+                for (int j = 0; j < 4; ++j) {
+                    o[j] = ln ? rstd[r] * (g[r][v][j] - s1 - xh[v][j] * s2) : g[r][v][j];
+                    c2[v][j] += o[j];
+                }
+                st4(gy + row * H + (lane + v * 32) * 4, o);
+            }
         }
     }
 
@@ -172,48 +200,49 @@ __global__ void __launch_bounds__(kEbThreads) k_epilogue_bwd(const EbArgs p) {
         for (int j = 0; j < 4; ++j) {
             red[wid][0][c + j] = c0[v][j];
             red[wid][1][c + j] = c1[v][j];
+            red[wid][2][c + j] = c2[v][j];
         }
     }
     if (lane == 0) red_b[wid] = sum_gr;
     __syncthreads();
     for (int c = threadIdx.x; c < H; c += kEbThreads) {
-        float a = 0.f, b = 0.f;
+        float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
         for (int w = 0; w < kEbWarps; ++w) {
             a += red[w][0][c];
             b += red[w][1][c];
+            d += red[w][2][c];
         }
-        p.part[((int64_t)blockIdx.x * 3 + 0) * H + c] = a;
-        p.part[((int64_t)blockIdx.x * 3 + 1) * H + c] = b;
+        p.part[((int64_t)blockIdx.x * 4 + 0) * H + c] = a;
+        p.part[((int64_t)blockIdx.x * 4 + 1) * H + c] = b;
+        p.part[((int64_t)blockIdx.x * 4 + 3) * H + c] = d;
     }
     if (threadIdx.x == 0) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kEbWarps; ++w) s += red_b[w];
-        p.part[((int64_t)blockIdx.x * 3 + 2) * H] = s;
+        p.part[((int64_t)blockIdx.x * 4 + 2) * H] = s;
     }
 }
 
-__global__ void k_epilogue_bwd_reduce(const float* __restrict__ part, int blocks, int H, float* __restrict__ o0,
-                                      float* __restrict__ o1, float* __restrict__ o2) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < H) {
-        float a = 0.f, b = 0.f;
-        for (int k = 0; k < blocks; ++k) {
-            a += part[((int64_t)k * 3 + 0) * H + c];
-            b += part[((int64_t)k * 3 + 1) * H + c];
-        }
-        if (o0) o0[c] = a;
-        if (o1) o1[c] = b;
-    }
-    if (c == 0 && o2) {
-        float s = 0.f;
-        for (int k = 0; k < blocks; ++k) s += part[((int64_t)k * 3 + 2) * H];
-        o2[0] = s;
-    }
+// Second pass of the column reductions: one WARP per (slot, column); lanes stride over the per-block partials and
+// a fixed shuffle tree combines them (deterministic).  A thread-per-column loop over ~600 partials is a chain of
+// ~600 dependent L2 loads and took longer than the main kernel.
+__global__ void __launch_bounds__(256) k_epilogue_bwd_reduce(const float* __restrict__ part, int blocks, int H, float* __restrict__ o0,
+                                                              float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ o3) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp id = slot * H + column
+    if (w >= 4 * H) return;
+    const int slot = w / H, c = w % H;
+    float* out = slot == 0 ? o0 : (slot == 1 ? o1 : (slot == 2 ? o2 : o3));
+    if (!out || (slot == 2 && c != 0)) return;
+    float s = 0.f;
+    for (int k = lane; k < blocks; k += 32) s += part[((int64_t)k * 4 + slot) * H + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = s;
 }
 
-int eb_blocks(int64_t N) { return (int)std::max<int64_t>(1, std::min<int64_t>((N + kEbWarps - 1) / kEbWarps, kEbMaxBlocks)); }
+int eb_blocks(int64_t N) { return (int)std::max<int64_t>(1, std::min<int64_t>((N + kEbWarps * 4 - 1) / (kEbWarps * 4), kEbMaxBlocks)); }
 
 // ---- masked MSE ----------------------------------------------------------------------------
 constexpr int kMseThreads = 256;
@@ -289,14 +318,14 @@ extern "C" int dfw_abi_version(void) { return 1; }
 
 extern "C" size_t dfw_epilogue_bwd_ws_bytes(int64_t N, int64_t Hout) {
     if (N < 0 || Hout < 1) return 0;
-    return dfw::align_up(sizeof(float) * 3 * (size_t)Hout * dfw::eb_blocks(N), 256);
+    return dfw::align_up(sizeof(float) * 4 * (size_t)Hout * dfw::eb_blocks(N), 256);
 }
 
 extern "C" int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const float* rowdot_w, const void* pre_out,
                                 const float* ln_stats, const void* act, const float* ln_gamma, const float* ln_beta,
                                 float dropout_p, uint64_t seed, void* g_y, float* dgamma, float* dbeta,
-                                float* d_rowdot_w, float* d_rowdot_b, int64_t N, int64_t Hout, int flags, int dtype,
-                                void* ws, size_t ws_bytes, dfw_stream_t stream) {
+                                float* d_rowdot_w, float* d_rowdot_b, float* d_bias, int64_t N, int64_t Hout, int flags,
+                                int dtype, void* ws, size_t ws_bytes, dfw_stream_t stream) {
     using namespace dfw;
     DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_epilogue_bwd: unknown dtype %d", dtype);
     DFW_REQUIRE(N >= 0 && Hout >= 4 && Hout <= 256 && Hout % 4 == 0,
@@ -309,7 +338,7 @@ extern "C" int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const 
     DFW_REQUIRE(ln || !(flags & DFW_EP_RELU) || act, "dfw_epilogue_bwd: ReLU backward needs act (or LayerNorm inputs)");
     DFW_REQUIRE(!(ln && g_rowdot), "dfw_epilogue_bwd: rowdot with LayerNorm is not a model configuration");
     if ((flags & DFW_EP_DROPOUT) && dropout_p == 0.f) flags &= ~DFW_EP_DROPOUT;
-    const bool need_cols = (ln && (dgamma || dbeta)) || (g_rowdot && (d_rowdot_w || d_rowdot_b));
+    const bool need_cols = (ln && (dgamma || dbeta)) || (g_rowdot && (d_rowdot_w || d_rowdot_b)) || d_bias;
     const int blocks = eb_blocks(N);
     if (need_cols) DFW_REQUIRE(ws && ws_bytes >= dfw_epilogue_bwd_ws_bytes(N, Hout), "dfw_epilogue_bwd: workspace too small");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -320,15 +349,20 @@ extern "C" int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const 
     a.g_y = g_y; a.part = need_cols ? reinterpret_cast<float*>(ws) : nullptr;
     a.N = N; a.H = (int)Hout; a.flags = flags;
     if (N > 0) {
-        if (dtype == DFW_F32) k_epilogue_bwd<float><<<blocks, kEbThreads, 0, s>>>(a);
-        else k_epilogue_bwd<__nv_bfloat16><<<blocks, kEbThreads, 0, s>>>(a);
+        if (Hout <= 128) {
+            if (dtype == DFW_F32) k_epilogue_bwd<float, 1><<<blocks, kEbThreads, 0, s>>>(a);
+            else k_epilogue_bwd<__nv_bfloat16, 1><<<blocks, kEbThreads, 0, s>>>(a);
+        } else {
+            if (dtype == DFW_F32) k_epilogue_bwd<float, 2><<<blocks, kEbThreads, 0, s>>>(a);
+            else k_epilogue_bwd<__nv_bfloat16, 2><<<blocks, kEbThreads, 0, s>>>(a);
+        }
         DFW_LAUNCH_CHECK();
     }
     if (need_cols) {
         float* o0 = ln ? dgamma : d_rowdot_w;
         float* o1 = ln ? dbeta : nullptr;
         float* o2 = g_rowdot ? d_rowdot_b : nullptr;
-        k_epilogue_bwd_reduce<<<(unsigned)((Hout + 127) / 128), 128, 0, s>>>(a.part, N > 0 ? blocks : 0, (int)Hout, o0, o1, o2);
+        k_epilogue_bwd_reduce<<<(unsigned)((4 * Hout * 32 + 255) / 256), 256, 0, s>>>(a.part, N > 0 ? blocks : 0, (int)Hout, o0, o1, o2, d_bias);
         DFW_LAUNCH_CHECK();
     }
     return 0;

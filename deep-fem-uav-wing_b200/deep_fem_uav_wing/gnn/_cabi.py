@@ -30,7 +30,7 @@ SIGNATURES = {
     "dfw_linear_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "dfw_epilogue_bwd_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "dfw_epilogue_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                 c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                  c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "dfw_linear_bwd_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
                                      c_void_p, c_size_t, c_void_p]),

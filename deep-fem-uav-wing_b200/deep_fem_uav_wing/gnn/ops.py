@@ -257,7 +257,7 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=Fals
 
 
 def epilogue_bwd(g_out, N, Hout, dtype_like, *, g_rowdot=None, rowdot_w=None, pre=None, stats=None, act=None, ln=None,
-                 relu=False, dropout_p=0.0, seed=0):
+                 relu=False, dropout_p=0.0, seed=0, want_bias_grad=False):
     dev = dtype_like.device
     flags = (EP_RELU if relu else 0) | (EP_LAYERNORM if ln is not None else 0) | (EP_DROPOUT if dropout_p > 0.0 else 0)
     g_y = torch.empty(N, Hout, dtype=dtype_like.dtype, device=dev)
@@ -268,6 +268,7 @@ def epilogue_bwd(g_out, N, Hout, dtype_like, *, g_rowdot=None, rowdot_w=None, pr
     if g_rowdot is not None:
         d_rw = torch.empty(Hout, dtype=torch.float32, device=dev)
         d_rb = torch.empty(1, dtype=torch.float32, device=dev)
+    d_bias = torch.empty(Hout, dtype=torch.float32, device=dev) if want_bias_grad else None
     ws_bytes = lib.dfw_epilogue_bwd_ws_bytes(N, Hout)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     es = 4 if dtype_like.dtype == torch.float32 else 2
@@ -276,10 +277,10 @@ def epilogue_bwd(g_out, N, Hout, dtype_like, *, g_rowdot=None, rowdot_w=None, pr
         check(lib.dfw_epilogue_bwd(
             _ptr(g_out), _ptr(g_rowdot), _ptr(rowdot_w), _ptr(pre), _ptr(stats), _ptr(act),
             _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(dropout_p),
-            int(seed) & 0xFFFFFFFFFFFFFFFF, g_y.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(d_rw), _ptr(d_rb), N, Hout, flags,
+            int(seed) & 0xFFFFFFFFFFFFFFFF, g_y.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(d_rw), _ptr(d_rb), _ptr(d_bias), N, Hout, flags,
             _DTYPES[dtype_like.dtype], ws.data_ptr(), ws_bytes, _stream(dtype_like)))
-    LAUNCH_COUNTER["kernels"] += 2 if (ln is not None or g_rowdot is not None) else 1
-    return g_y, dgamma, dbeta, d_rw, d_rb
+    LAUNCH_COUNTER["kernels"] += 2 if (ln is not None or g_rowdot is not None or want_bias_grad) else 1
+    return g_y, dgamma, dbeta, d_rw, d_rb, d_bias
 
 
 def linear_bwd_input(g_y, w, row_scale=None, addend=None):
@@ -390,13 +391,15 @@ class SageConvFn(torch.autograd.Function):
         graph: CSRGraph = ctx.graph
         g_out = g_out.contiguous()
         N, H = g_out.shape
-        dgamma = dbeta = None
+        dgamma = dbeta = dbl = None
         if ctx.fused_tail:
-            g_y, dgamma, dbeta, _, _ = epilogue_bwd(g_out, N, H, g_out, pre=pre, stats=stats, ln=(gamma, beta), relu=True,
-                                                    dropout_p=ctx.dropout_p, seed=ctx.seed)
+            # the epilogue backward also emits the column sums of g_y = lin_l's bias gradient
+            g_y, dgamma, dbeta, _, _, dbl = epilogue_bwd(g_out, N, H, g_out, pre=pre, stats=stats, ln=(gamma, beta), relu=True,
+                                                         dropout_p=ctx.dropout_p, seed=ctx.seed, want_bias_grad=ctx.has_bias)
+            dwl, dwr, _ = linear_bwd_weight(g_y, agg, x, want_bias=False)
         else:
             g_y = g_out
-        dwl, dwr, dbl = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias)
+            dwl, dwr, dbl = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias)
         g_x = None
         if ctx.needs_input_grad[0]:
             g_agg = linear_bwd_input(g_y, wl, row_scale=graph.inv_deg)
@@ -430,10 +433,12 @@ class LinearFn(torch.autograd.Function):
         if ctx.relu or ctx.dropout_p > 0.0:
             if H % 4 != 0:
                 raise RuntimeError("dfw_b200: ReLU/dropout backward needs out_features % 4 == 0")
-            g_y, _, _, _, _ = epilogue_bwd(g_out, N, H, g_out, act=act, relu=ctx.relu, dropout_p=ctx.dropout_p, seed=ctx.seed)
+            g_y, _, _, _, _, db = epilogue_bwd(g_out, N, H, g_out, act=act, relu=ctx.relu, dropout_p=ctx.dropout_p, seed=ctx.seed,
+                                               want_bias_grad=ctx.has_bias)
+            dw, _, _ = linear_bwd_weight(g_y, x, None, want_bias=False)
         else:
             g_y = g_out
-        dw, _, db = linear_bwd_weight(g_y, x, None, want_bias=ctx.has_bias)
+            dw, _, db = linear_bwd_weight(g_y, x, None, want_bias=ctx.has_bias)
         g_x = linear_bwd_input(g_y, wc) if ctx.needs_input_grad[0] else None
         return g_x, dw, db, None, None, None
 
@@ -468,9 +473,9 @@ class DecoderTailFn(torch.autograd.Function):
         N = h.shape[0]
         Hmid = hid.shape[1]
         g_r = g_out.reshape(-1).float().contiguous()
-        g_y, _, _, dw4, db4 = epilogue_bwd(None, N, Hmid, hid, g_rowdot=g_r, rowdot_w=w4f, act=hid, relu=True,
-                                           dropout_p=ctx.dropout_p, seed=ctx.seed)
-        dw3, _, db3 = linear_bwd_weight(g_y, h, None, want_bias=ctx.has_b3)
+        g_y, _, _, dw4, db4, db3 = epilogue_bwd(None, N, Hmid, hid, g_rowdot=g_r, rowdot_w=w4f, act=hid, relu=True,
+                                                dropout_p=ctx.dropout_p, seed=ctx.seed, want_bias_grad=ctx.has_b3)
+        dw3, _, _ = linear_bwd_weight(g_y, h, None, want_bias=False)
         g_h = linear_bwd_input(g_y, w3c) if ctx.needs_input_grad[0] else None
         return g_h, dw3, db3, dw4.reshape(1, -1), (db4 if ctx.has_b4 else None), None, None
 

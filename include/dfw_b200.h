@@ -104,14 +104,15 @@ int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1,
  *      Without DFW_EP_LAYERNORM, `act` (the saved post-ReLU output) gives the ReLU mask.
  *      dgamma/dbeta fp32 [Hout] (LayerNorm only).  ws: dfw_epilogue_bwd_ws_bytes.
  *      rowdot variant: g_rowdot fp32 [N] (dL/d rowdot_out) replaces g_out, and
- *      d_rowdot_w [Hout], d_rowdot_b [1] are produced.
+ *      d_rowdot_w [Hout], d_rowdot_b [1] are produced.  d_bias (nullable, fp32 [Hout]) receives the column sums
+ *      of g_y, i.e. the bias gradient of the linear that produced y (saves a pass in (d3)).
  * ---------------------------------------------------------------------------------------- */
 size_t dfw_epilogue_bwd_ws_bytes(int64_t N, int64_t Hout);
 int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const float* rowdot_w,
                      const void* pre_out, const float* ln_stats, const void* act,
                      const float* ln_gamma, const float* ln_beta,
                      float dropout_p, uint64_t seed,
-                     void* g_y, float* dgamma, float* dbeta, float* d_rowdot_w, float* d_rowdot_b,
+                     void* g_y, float* dgamma, float* dbeta, float* d_rowdot_w, float* d_rowdot_b, float* d_bias,
                      int64_t N, int64_t Hout, int flags, int dtype,
                      void* ws, size_t ws_bytes, dfw_stream_t stream);
 
