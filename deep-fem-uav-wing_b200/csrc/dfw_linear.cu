@@ -608,9 +608,9 @@ DwPlan dw_plan(int64_t N, int64_t Hout, int64_t k1, int64_t k2) {
 // tensor-core variant: one CTA per [128 x 128] tile and node slice, ~one CTA per SM in total
 DwPlan dw_plan_tc(int64_t N, int64_t Hout, int64_t k1, int64_t k2) {
     DwPlan p;
-    p.tiles_i = (int)(Hout / 128);
-    p.tiles_j1 = (int)(k1 / 128);
-    p.tiles_j2 = (int)(k2 / 128);
+    p.tiles_i = (int)((Hout + 127) / 128);
+    p.tiles_j1 = (int)((k1 + 127) / 128);
+    p.tiles_j2 = (int)((k2 + 127) / 128);
     const int tiles = std::max(1, p.tiles_i * (p.tiles_j1 + p.tiles_j2));
     int64_t splits = std::max<int64_t>(1, kNumSMs / tiles);
     int64_t per = (N + splits - 1) / splits;
@@ -629,7 +629,7 @@ extern "C" size_t dfw_linear_bwd_weight_ws_bytes(int64_t N, int64_t Hout, int64_
     if (N < 0 || Hout < 1 || k1 < 1 || k2 < 0) return 0;
     dfw::DwPlan p = dfw::dw_plan(N, Hout, k1, k2);
     size_t need = p.part_bytes + p.db_bytes;
-    if (Hout % 128 == 0 && k1 % 128 == 0 && k2 % 128 == 0) {
+    if (Hout % 32 == 0 && k1 % 32 == 0 && k2 % 32 == 0) {
         dfw::DwPlan t = dfw::dw_plan_tc(N, Hout, k1, k2);
         need = std::max(need, t.part_bytes + t.db_bytes);
     }

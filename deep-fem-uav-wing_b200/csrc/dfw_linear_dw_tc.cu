@@ -39,6 +39,7 @@ struct DwArgs {
     int64_t nodes_per_split;  // multiple of kDwNodes
     int tiles_j[2];           // 128-feature column tiles of a1 / a2
     int k[2];
+    int Hout;
     int stages;
     float* part;              // [splits][tiles][128][128]
 };
@@ -82,6 +83,23 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
     const int64_t node_beg = (int64_t)blockIdx.y * p.nodes_per_split;
     const int64_t node_end = min(p.N, node_beg + p.nodes_per_split);
     const int nsteps = node_end > node_beg ? (int)((node_end - node_beg + kDwNodes - 1) / kDwNodes) : 0;
+    // ragged tiles: only the 128-byte feature blocks that exist are fetched.  Missing M blocks (Hout < 128) are
+    // zero-filled once (the MMA always covers M = 128); missing N blocks simply shrink the instruction's N.
+    const int mb_valid = min(NB, (p.Hout - ti * kDwTile + EPB - 1) / EPB);
+    const int nb_valid = min(NB, (p.k[which] - tj * kDwTile + EPB - 1) / EPB);
+    const int n_cols = nb_valid * EPB;
+    if (mb_valid < NB) {
+        for (int s = 0; s < p.stages; ++s) {
+            uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * STAGE + G_HI + mb_valid * BOX);
+            const int n16 = (NB - mb_valid) * (int)BOX / 16;
+            for (int i = threadIdx.x; i < n16; i += kDwThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (TF32) {
+                uint4* zl = reinterpret_cast<uint4*>(smem + (size_t)s * STAGE + G_LO + mb_valid * BOX);
+                for (int i = threadIdx.x; i < n16; i += kDwThreads) zl[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        fence_proxy_async();
+    }
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.g);
@@ -113,11 +131,11 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
                 const int node0 = (int)(node_beg + (int64_t)it * kDwNodes);
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* st = smem + (size_t)stage * STAGE;
-                mbar_arrive_expect_tx(&full[stage], 2 * OPER);
+                mbar_arrive_expect_tx(&full[stage], (uint32_t)(mb_valid + nb_valid) * BOX);
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    tma_load_2d(st + G_HI + b * BOX, &maps.g, &full[stage], ti * kDwTile + b * EPB, node0);
-                    tma_load_2d(st + A_HI + b * BOX, &maps.a[which], &full[stage], tj * kDwTile + b * EPB, node0);
+                    if (b < mb_valid) tma_load_2d(st + G_HI + b * BOX, &maps.g, &full[stage], ti * kDwTile + b * EPB, node0);
+                    if (b < nb_valid) tma_load_2d(st + A_HI + b * BOX, &maps.a[which], &full[stage], tj * kDwTile + b * EPB, node0);
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -126,7 +144,7 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
         if (lane == 0) {
             // F32 accumulate | a/b format | A and B MN-major (bits 15, 16) | N = 128 | M = 128
             const uint32_t fmt = TF32 ? 2u : 1u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(kDwTile >> 3) << 17) |
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n_cols >> 3) << 17) |
                                    ((uint32_t)(kDwTile >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0, accumulate = 0;
@@ -203,6 +221,7 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
             const bool two_main = nsteps * (kDwNodes / KSTEP_NODES) >= 2;
 #pragma unroll
             for (int c0 = 0; c0 < kDwTile; c0 += 32) {
+                if (c0 >= n_cols) break;  // columns beyond the instruction's N were never written
                 float v[32];
                 tmem_ld32(t_row + c0, v);
                 if (TF32) {  // round-to-nearest sum of the accumulators (see tmem_combine)
@@ -277,9 +296,9 @@ __global__ void __launch_bounds__(256) k_colsum_final(const float* __restrict__ 
 }  // namespace tc
 
 bool dw_tc_eligible(int64_t N, int64_t Hout, int64_t k1, int64_t k2, int dtype, const void* g, const void* a1, const void* a2) {
-    if (N < 1 || N >= (1LL << 31) || Hout % 128 || Hout > 256) return false;
-    if (k1 % 128 || (a2 && k2 % 128)) return false;
-    (void)dtype;
+    const int epb = dtype == DFW_F32 ? 32 : 64;  // features per 128-byte block
+    if (N < 1 || N >= (1LL << 31) || Hout % epb || Hout > 256 || Hout < 32) return false;
+    if (k1 % epb || k1 < 32 || (a2 && (k2 % epb || k2 < 32))) return false;
     return aligned16(g) && aligned16(a1) && (!a2 || aligned16(a2));
 }
 
@@ -297,15 +316,16 @@ int dw_tc_launch(const void* g_y, const void* a1, int64_t k1, const void* a2, in
     DwArgs p{};
     p.N = N;
     p.nodes_per_split = nodes_per_split;
-    p.tiles_j[0] = (int)(k1 / kDwTile);
-    p.tiles_j[1] = a2 ? (int)(k2 / kDwTile) : 0;
+    p.tiles_j[0] = (int)((k1 + kDwTile - 1) / kDwTile);
+    p.tiles_j[1] = a2 ? (int)((k2 + kDwTile - 1) / kDwTile) : 0;
     p.k[0] = (int)k1;
     p.k[1] = (int)k2;
+    p.Hout = (int)Hout;
     p.part = part;
     const uint32_t stage = (tf32 ? 4u : 2u) * (uint32_t)(kDwTile * e / kChunkBytes) * kDwNodes * kChunkBytes;
     p.stages = tf32 ? 3 : 4;  // 3 x 64 KB (fp32) / 4 x 16 KB (bf16)
     const size_t smem = (size_t)p.stages * stage + 8 * (3 * kDwMaxStages + 1) + 16 + 1024;
-    dim3 grid((unsigned)((Hout / kDwTile) * (p.tiles_j[0] + p.tiles_j[1])), (unsigned)splits, 1);
+    dim3 grid((unsigned)(((Hout + kDwTile - 1) / kDwTile) * (p.tiles_j[0] + p.tiles_j[1])), (unsigned)splits, 1);
     if (tf32) {
         auto kern = k_dw_tc<float, true>;
         DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -153,7 +153,8 @@ def _ref_linear(a1, w1, a2, w2, b, ln, relu, res):
     return y, out
 
 
-@pytest.mark.parametrize("hout,k1,k2", [(64, 10, 0), (128, 64, 0), (64, 64, 64), (128, 128, 128), (256, 256, 256), (16, 16, 16), (64, 128, 0)])
+@pytest.mark.parametrize("hout,k1,k2", [(64, 10, 0), (128, 64, 0), (64, 64, 64), (128, 128, 128), (256, 256, 256), (16, 16, 16), (64, 128, 0),
+                                        (192, 64, 192)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_linear_fwd_and_bwd_pieces(ops, hout, k1, k2, dtype):
     torch.manual_seed(hout + k1)
