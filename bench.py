@@ -182,7 +182,7 @@ def cpu_info():
     return {"os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads(), "cpu_model": model}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
@@ -199,7 +199,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -228,9 +228,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner) write to fd 1 too, so
+    # everything else is routed to stderr and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
 
     import torch.distributed as dist
@@ -265,7 +273,7 @@ def main():
     opt = torch.optim.AdamW(model.parameters(), lr=LR, weight_decay=WD, fused=True)
     crit = MaskedMSELoss()
 
-    def train_step(b, read_loss=False):
+    def train_step(b, read_loss=False, return_loss=False):
         if ddp is not None:
             ddp.zero_grad()
         else:
@@ -278,6 +286,8 @@ def main():
         else:
             loss.backward()
         opt.step()
+        if return_loss:
+            return loss.detach()
         return loss.item() if read_loss else None
 
     # ---- arm 1: device-resident batches, CSR cached (one-time build per batch) -----------------
@@ -334,11 +344,31 @@ def main():
         ops.clear_graph_cache()
         for _ in range(warmup):
             train_step(next(it), read_loss=True)
-        ms_e2e = timed_region(lambda i: train_step(next(it), read_loss=True), steps, dist_on, device)
+        # every step's loss is read back on the host inside the timed region; the read of step i happens after
+        # step i+1 has been enqueued (one-step software pipeline), so the GPU is never idle while Python launches
+        loss_pin = torch.empty(steps, dtype=torch.float32).pin_memory()
+        loss_evs, loss_vals = [], []
+
+        def e2e_step(i):
+            loss = train_step(next(it), return_loss=True)
+            loss_pin[i:i + 1].copy_(loss.reshape(1).float(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            loss_evs.append(ev)
+            if i > 0:
+                loss_evs[i - 1].synchronize()
+                loss_vals.append(float(loss_pin[i - 1]))
+            if i == steps - 1:
+                ev.synchronize()
+                loss_vals.append(float(loss_pin[i]))
+
+        ms_e2e = timed_region(e2e_step, steps, dist_on, device)
+        assert len(loss_vals) == steps and all(np.isfinite(loss_vals)), "e2e losses were not all read back"
         e2e = {"value": BATCH * steps * world / (ms_e2e * 1e-3), "unit": "meshes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / steps,
                "path": "DataLoader(pinned host Data, device=cuda) -> H2D on a copy stream (1 batch prefetch) -> GraphSAGEModel(x, edge_index, batch) "
-                       "incl. on-device CSR build -> MaskedMSELoss -> backward -> AdamW -> loss.item()"}
+                       "incl. on-device CSR build -> MaskedMSELoss -> backward -> AdamW -> loss copied to pinned host memory and read "
+                       "(every step, one step behind the launch front)"}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
@@ -357,7 +387,7 @@ def main():
             "nodes_per_sec": value * NODES, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()

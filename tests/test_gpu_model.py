@@ -220,3 +220,22 @@ def test_training_step_reduces_loss_and_checkpoint_roundtrip(tmp_path):
     model.eval()
     with torch.no_grad():
         assert rel_max(model(x, ei).cpu(), ref(x.cpu(), ei.cpu())) < 10 * TOL_FP32
+
+
+def test_prefetching_loader_matches_host_collation():
+    """DataLoader(device=cuda): per-mesh async H2D + on-device offsets must equal the host-side disjoint union."""
+    from deep_fem_uav_wing.gnn import synth
+    from deep_fem_uav_wing.gnn.loader import Batch, Data, DataLoader
+
+    datas = []
+    for s in range(5):
+        m = synth.surface_tri_wing(800 + 100 * s, seed=s)
+        datas.append(Data(x=torch.from_numpy(m["x"]), edge_index=torch.from_numpy(m["edge_index"]), y=torch.from_numpy(m["y"]),
+                          loss_mask=torch.from_numpy(m["loss_mask"])))
+    host = list(DataLoader(datas, batch_size=2, shuffle=False))
+    dev = list(DataLoader(datas, batch_size=2, shuffle=False, device="cuda"))
+    assert len(host) == len(dev) == 3
+    for h, d in zip(host, dev):
+        assert d.x.is_cuda and d.num_graphs == h.num_graphs
+        for k in ("x", "edge_index", "y", "loss_mask", "ptr", "batch"):
+            assert torch.equal(getattr(d, k).cpu(), getattr(h, k)), k
