@@ -1,0 +1,168 @@
+#!/usr/bin/env python3
+"""Secondary workloads of BASELINE.json (configs 1, 4, 5) - one JSON line each.  bench.py is the headline (config 2/3).
+
+    python tools/bench_configs.py cfg1        # H=64, L=3 inference on one 20k-node mesh (tri and tet) + parity vs the CPU oracle
+    python tools/bench_configs.py cfg4        # 2M-node / ~27M-edge tet mesh, H=256, bf16 inference: aggregation roofline + forward
+    python tools/bench_configs.py cfg5 [N]    # design-screening batch inference: N meshes of 20k nodes, H=128, L=4 (fp32 + bf16)
+    torchrun --nproc-per-node G tools/bench_configs.py cfg5 N   # sharded over G GPUs, no communication
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path[:0] = [REPO, os.path.join(REPO, "deep-fem-uav-wing_b200")]
+from deep_fem_uav_wing.gnn import ops, synth  # noqa: E402
+from deep_fem_uav_wing.gnn.loader import Batch, Data  # noqa: E402
+from deep_fem_uav_wing.gnn.model import GraphSAGEModel  # noqa: E402
+
+PEAK = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6650.0
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def gpu_time(fn, iters=20, warm=3, flush=True):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[len(ts) // 10], ts[-1 - len(ts) // 10]
+
+
+def cfg1():
+    from oracle.sage_oracle import GraphSAGEModelRef
+
+    for kind, gen in (("tri", synth.surface_tri_wing), ("tet", synth.tet_lattice_wing)):
+        mesh = gen(20000, seed=42)
+        torch.manual_seed(42)
+        ref = GraphSAGEModelRef(10, 64, 1, 3).eval()
+        model = GraphSAGEModel(10, 64, 1, 3)
+        model.load_state_dict(ref.state_dict())
+        model = model.cuda().eval()
+        x, ei = torch.from_numpy(mesh["x"]), torch.from_numpy(mesh["edge_index"])
+        torch.set_num_threads(os.cpu_count())
+        with torch.no_grad():
+            for _ in range(3):
+                out_ref = ref(x, ei)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                out_ref = ref(x, ei)
+            cpu_s = (time.perf_counter() - t0) / 10
+            xd, eid = x.cuda(), ei.cuda()
+            out = model(xd, eid)
+            err = ((out.cpu() - out_ref).abs().max() / out_ref.abs().max()).item()
+            med, p10, p90 = gpu_time(lambda: model(xd, eid), flush=False)
+        print(json.dumps({"config": f"cfg1-{kind}", "N": mesh["num_nodes"], "E": int(ei.shape[1]), "hidden": 64, "layers": 3, "dtype": "f32",
+                          "gpu_forward_us": round(med * 1e6, 1), "gpu_p10_us": round(p10 * 1e6, 1), "gpu_p90_us": round(p90 * 1e6, 1),
+                          "gpu_nodes_per_s": mesh["num_nodes"] / med, "cpu_forward_ms": round(cpu_s * 1e3, 2), "cpu_threads": torch.get_num_threads(),
+                          "speedup_vs_cpu_oracle": cpu_s / med, "fwd_rel_err_vs_oracle": err, "note": "CSR cached (one-time build); L2-resident mesh"}), flush=True)
+
+
+def cfg4():
+    for order in ("native", "random"):
+        mesh = synth.tet_lattice_wing(2_000_000, seed=42, node_order=order, shuffle_edges=False)
+        n = mesh["num_nodes"]
+        ei = torch.from_numpy(mesh["edge_index"]).cuda()
+        E = int(ei.shape[1])
+        t0 = time.perf_counter()
+        g = ops.get_graph(ei, n)
+        torch.cuda.synchronize()
+        csr_s = time.perf_counter() - t0
+        H = 256
+        x = torch.randn(n, H, device="cuda").bfloat16()
+        amin = 2 * n * H * 2 + 4 * E + 4 * (n + 1)
+        agather = E * H * 2 + n * H * 2 + 4 * E + 4 * (n + 1)
+        med, p10, p90 = gpu_time(lambda: ops.aggregate(g.rowptr, g.col, g.inv_deg, x))
+        line = {"config": f"cfg4-{order}", "N": n, "E": E, "hidden": H, "dtype": "bf16", "lattice": mesh["lattice_dims"],
+                "aggregate_us": round(med * 1e6, 1), "aggregate_p10_us": round(p10 * 1e6, 1), "aggregate_p90_us": round(p90 * 1e6, 1),
+                "A_min_MB": round(amin / 1e6, 1), "A_gather_MB": round(agather / 1e6, 1), "achieved_GBps_on_A_min": round(amin / med / 1e9, 1),
+                "hbm_frac_on_A_min": round(amin / med / 1e9 / PEAK, 4), "peak_GBps": PEAK, "csr_build_ms_incl_host": round(csr_s * 1e3, 2)}
+        torch.manual_seed(0)
+        model = GraphSAGEModel(10, H, 1, 3).cuda().eval().set_compute_dtype(torch.bfloat16)
+        xin = torch.from_numpy(mesh["x"]).cuda()
+        with torch.no_grad():
+            fmed, _, _ = gpu_time(lambda: model(xin, ei), iters=10)
+        line.update({"forward_L3_ms": round(fmed * 1e3, 3), "forward_nodes_per_s": n / fmed})
+        print(json.dumps(line), flush=True)
+        del g, x, model
+        ops.clear_graph_cache()
+        torch.cuda.empty_cache()
+
+
+def cfg5(n_meshes):
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ids = list(range(rank, n_meshes, world))  # case list sharded round-robin: no communication
+    uniq = [synth.surface_tri_wing(20000, seed=42 + i) for i in range(min(len(ids), 64))]  # 64 distinct meshes, cycled
+    datas = [Data(x=torch.from_numpy(m["x"]), edge_index=torch.from_numpy(m["edge_index"])) for m in uniq]
+    per_launch = 16
+    results = {}
+    for dt_name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        torch.manual_seed(42)
+        model = GraphSAGEModel(10, 128, 1, 4).cuda().eval().set_compute_dtype(dt)
+        batches = []
+        for s in range(0, len(datas), per_launch):
+            b = Batch.from_data_list(datas[s:s + per_launch]).to("cuda")
+            ops.get_graph(b.edge_index, b.x.shape[0])
+            batches.append(b)
+        n_launch = (len(ids) + per_launch - 1) // per_launch
+        with torch.no_grad():
+            for i in range(3):
+                model(batches[i % len(batches)].x, batches[i % len(batches)].edge_index)
+            torch.cuda.synchronize()
+            if dist_on:
+                dist.barrier()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            outs = []
+            for i in range(n_launch):
+                bb = batches[i % len(batches)]
+                outs.append(model(bb.x, bb.edge_index)[:1])
+            b_.record()
+            torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b_)], dtype=torch.float64, device="cuda")
+        if dist_on:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        results[dt_name] = {"meshes_per_s": n_meshes / (ms.item() * 1e-3), "ms_total": ms.item()}
+    if rank == 0:
+        print(json.dumps({"config": "cfg5", "n_meshes": n_meshes, "nodes_per_mesh": 20000, "hidden": 128, "layers": 4, "n_gpus": world,
+                          "meshes_per_launch": per_launch, "sharding": "case list round-robin over ranks, no communication",
+                          "data": "64 distinct synthetic meshes per rank cycled, device resident, CSR cached", **results}), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "cfg1"
+    if what == "cfg1":
+        cfg1()
+    elif what == "cfg4":
+        cfg4()
+    elif what == "cfg5":
+        cfg5(int(sys.argv[2]) if len(sys.argv) > 2 else 1250)
