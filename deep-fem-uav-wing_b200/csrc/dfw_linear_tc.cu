@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             uint32_t acc_main[2] = {0u, 0u}, acc_cross = 0u;
             const uint32_t t_cross = tmem_base + (uint32_t)(p.nacc * p.Npad);
             const uint64_t dbase = make_desc_k<CB>(0);  // every field but the 14-bit start address
+            const bool stacked = TF32 && p.nacc == 1 && 2 * p.Npad <= 256 && L.w_lo == L.w_hi + (uint32_t)p.Npad * CB;
+            const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * p.Npad) >> 3) << 17);
             int kstep = 0;
             for (int c = 0; c < total_chunks; ++c) {
                 mbar_wait(TF32 ? &conv[stage] : &full[stage], phase);
@@ -189,13 +191,23 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                     if (TF32) {
                         const uint64_t a_lo = dbase + ((st + L.a_lo + k * 32) >> 4);
                         const uint64_t w_lo = dbase + ((st + L.w_lo + k * 32) >> 4);
-                        const int m = kstep % p.nacc;
-                        umma<TF32>(t_cross, a_lo, w_hi, idesc, acc_cross);
-                        umma<TF32>(t_cross, a_hi, w_lo, idesc, 1u);
-                        umma<TF32>(tmem_base + (uint32_t)(m * p.Npad), a_hi, w_hi, idesc, acc_main[m]);
-                        acc_cross = 1u;
-                        acc_main[m] = 1u;
-                        ++kstep;
+                        if (stacked) {
+                            // tcgen05.mma costs ~140 cycles per instruction here whatever N is (measured: issue/latency
+                            // bound, not MAC bound), so use fewer, wider instructions: w_lo sits right behind w_hi in
+                            // shared memory, hence ONE N = 2*Npad MMA yields a_hi.w_hi (columns [0,Npad): main accumulator)
+                            // and a_hi.w_lo (columns [Npad,2Npad): cross accumulator); a second N = Npad MMA adds a_lo.w_hi.
+                            umma<TF32>(tmem_base, a_hi, w_hi, idesc2, acc_cross);
+                            umma<TF32>(t_cross, a_lo, w_hi, idesc, 1u);
+                            acc_cross = 1u;
+                        } else {
+                            const int m = kstep % p.nacc;
+                            umma<TF32>(t_cross, a_lo, w_hi, idesc, acc_cross);
+                            umma<TF32>(t_cross, a_hi, w_lo, idesc, 1u);
+                            umma<TF32>(tmem_base + (uint32_t)(m * p.Npad), a_hi, w_hi, idesc, acc_main[m]);
+                            acc_cross = 1u;
+                            acc_main[m] = 1u;
+                            ++kstep;
+                        }
                     } else {
                         umma<TF32>(tmem_base, a_hi, w_hi, idesc, accumulate);
                     }

@@ -14,7 +14,7 @@ def run():
     from deep_fem_uav_wing.gnn import ops
 
     torch.manual_seed(0)
-    n = 20000
+    n = int(os.environ.get("NROWS", "20000"))
     for H in (64, 128, 256):
         a1 = torch.randn(n, H, device="cuda")
         a2 = torch.randn(n, H, device="cuda")
