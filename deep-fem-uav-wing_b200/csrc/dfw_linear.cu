@@ -502,6 +502,76 @@ inline dim3 grid_rows(int64_t N, int BM, int64_t ytiles = 1) { return dim3((unsi
 }  // namespace
 }  // namespace dfw
 
+
+// ---- tiny-K linears (the encoder's Linear(10, 64), model.py:53): pure streaming, no tiling needed ----------------
+namespace dfw {
+namespace {
+constexpr int kSmallKMax = 16;
+
+// out[n, c] = relu?(sum_k x[n,k] * w[c,k] + b[c]);  thread = (row, 4 output columns), weights in registers
+template <typename T>
+__global__ void __launch_bounds__(256) k_linear_smallk_fwd(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                                                            T* __restrict__ out, int64_t N, int K, int Hout, int relu) {
+    const int groups = Hout / 4;                       // column groups per row
+    const int rows_per_iter = blockDim.x / groups;     // rows handled by the block per iteration
+    const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+    if (rl >= rows_per_iter) return;
+    float wr[4][kSmallKMax], b4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        b4[j] = bias ? __ldg(bias + cg * 4 + j) : 0.f;
+#pragma unroll
+        for (int k = 0; k < kSmallKMax; ++k) wr[j][k] = k < K ? to_f32(w[(int64_t)(cg * 4 + j) * K + k]) : 0.f;
+    }
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rl; r < N; r += (int64_t)gridDim.x * rows_per_iter) {
+        float xv[kSmallKMax];
+#pragma unroll
+        for (int k = 0; k < kSmallKMax; ++k) xv[k] = k < K ? to_f32(x[r * K + k]) : 0.f;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = b4[j];
+#pragma unroll
+            for (int k = 0; k < kSmallKMax; ++k) a = fmaf(xv[k], wr[j][k], a);
+            o[j] = relu ? fmaxf(a, 0.f) : a;
+        }
+        store_row4(out, r, (int64_t)Hout, cg * 4, (int64_t)Hout, o, true);
+    }
+}
+
+// partial dW[i, k] over the block's rows: thread = (output row i, k-slot), two-pass like the big kernels
+template <typename T>
+__global__ void __launch_bounds__(256) k_linear_smallk_dw(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ part,
+                                                           int64_t N, int K, int Hout) {
+    // thread t: i = t % Hout (needs Hout <= 256), handles all K (<= 16) columns in registers
+    const int i = threadIdx.x;
+    if (i >= Hout) return;
+    float acc[kSmallKMax];
+#pragma unroll
+    for (int k = 0; k < kSmallKMax; ++k) acc[k] = 0.f;
+    const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(N, r0 + per);
+    for (int64_t r = r0; r < r1; ++r) {
+        const float gv = to_f32(g[r * Hout + i]);
+#pragma unroll
+        for (int k = 0; k < kSmallKMax; ++k)
+            if (k < K) acc[k] = fmaf(gv, to_f32(x[r * K + k]), acc[k]);
+    }
+    for (int k = 0; k < K; ++k) part[((int64_t)blockIdx.x * Hout + i) * K + k] = acc[k];
+}
+__global__ void __launch_bounds__(256) k_smallk_dw_reduce(const float* __restrict__ part, int blocks, int total, float* __restrict__ dw,
+                                                           int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp per output element, lanes stride over the partials
+    if (e >= total) return;
+    float s = 0.f;
+    for (int b = lane; b < blocks; b += 32) s += part[(int64_t)b * total + e];
+    s = warp_sum(s);
+    if (lane == 0) dw[e] = accumulate ? dw[e] + s : s;
+}
+}  // namespace
+}  // namespace dfw
+
 extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const void* a2, const void* w2, int64_t k2,
                               const float* bias, const float* ln_gamma, const float* ln_beta, float ln_eps,
                               const void* residual, float dropout_p, uint64_t seed, void* out, void* pre_out,
@@ -533,6 +603,21 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
         t.out = out; t.pre_out = pre_out; t.ln_stats = ln_stats;
         t.rowdot_w = rowdot_w; t.rowdot_b = rowdot_b; t.rowdot_out = rowdot_out;
         return linear_tc_launch(a1, w1, k1, a2, w2, k2, 0, t, dtype, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+    }
+    if (!force_simt() && !a2 && k1 <= kSmallKMax && Hout % 4 == 0 && Hout <= 1024 && out && !pre_out && !rowdot_out &&
+        !(flags & ~DFW_EP_RELU) && aligned16(out)) {
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        const int groups = (int)(Hout / 4);
+        const int threads = std::max(groups, 256 / groups * groups);
+        const int rows_per_iter = threads / groups;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((N + rows_per_iter - 1) / rows_per_iter, (int64_t)kNumSMs * 8));
+        if (dtype == DFW_F32)
+            k_linear_smallk_fwd<float><<<blocks, threads, 0, st>>>((const float*)a1, (const float*)w1, bias, (float*)out, N, (int)k1, (int)Hout, flags & DFW_EP_RELU);
+        else
+            k_linear_smallk_fwd<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)a1, (const __nv_bfloat16*)w1, bias, (__nv_bfloat16*)out, N,
+                                                                        (int)k1, (int)Hout, flags & DFW_EP_RELU);
+        DFW_LAUNCH_CHECK();
+        return 0;
     }
     LinArgs a{};
     a.a1 = a1; a.w1 = w1; a.k1 = k1; a.a2 = a2; a.w2 = w2; a.k2 = a2 ? k2 : 0;
@@ -663,6 +748,20 @@ extern "C" int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1
                                                     dw2, nullptr, accumulate);
         DFW_LAUNCH_CHECK();
         return 0;
+    }
+    if (N > 0 && !force_simt() && !a2 && !dbias && k1 <= kSmallKMax && Hout <= 256) {
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((N + 255) / 256, (int64_t)kNumSMs * 4));
+        const size_t need = sizeof(float) * (size_t)blocks * Hout * k1;
+        if (ws && ws_bytes >= need) {
+            float* part = reinterpret_cast<float*>(ws);
+            if (dtype == DFW_F32) k_linear_smallk_dw<float><<<blocks, 256, 0, s>>>((const float*)g_y, (const float*)a1, part, N, (int)k1, (int)Hout);
+            else k_linear_smallk_dw<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)g_y, (const __nv_bfloat16*)a1, part, N, (int)k1, (int)Hout);
+            DFW_LAUNCH_CHECK();
+            const int total = (int)(Hout * k1);
+            k_smallk_dw_reduce<<<(total * 32 + 255) / 256, 256, 0, s>>>(part, blocks, total, dw1, accumulate);
+            DFW_LAUNCH_CHECK();
+            return 0;
+        }
     }
     DwPlan pl = dw_plan(N, Hout, k1, k2);
     DFW_REQUIRE(ws && ws_bytes >= pl.part_bytes + pl.db_bytes, "dfw_linear_bwd_weight: workspace too small (%zu < %zu)",

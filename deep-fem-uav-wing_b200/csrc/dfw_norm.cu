@@ -279,13 +279,25 @@ __global__ void __launch_bounds__(kMseThreads) k_mse_fwd(const T* __restrict__ p
         last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {  // fixed-order final reduction by the whole last block (a single-thread loop took ~25 us)
         __threadfence();
         double a = 0.0, b = 0.0;
-        for (unsigned k = 0; k < gridDim.x; ++k) { a += (double)part[2 * k]; b += (double)part[2 * k + 1]; }
-        result[0] = (float)(mean ? a / (b > 1.0 ? b : 1.0) : a);
-        result[1] = (float)b;
-        *ticket = 0u;
+        for (unsigned k = threadIdx.x; k < gridDim.x; k += blockDim.x) { a += (double)part[2 * k]; b += (double)part[2 * k + 1]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        __shared__ double da[kMseThreads / 32], db[kMseThreads / 32];
+        if (lane == 0) { da[wid] = a; db[wid] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            a = 0.0; b = 0.0;
+            for (int w = 0; w < kMseThreads / 32; ++w) { a += da[w]; b += db[w]; }
+            result[0] = (float)(mean ? a / (b > 1.0 ? b : 1.0) : a);
+            result[1] = (float)b;
+            *ticket = 0u;
+        }
     }
 }
 
