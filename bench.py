@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--mesh", default="tri", choices=["tri", "tet"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="e2e arm: launch kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -270,7 +271,7 @@ def main():
     torch.manual_seed(42)
     model = GraphSAGEModel(10, HIDDEN, 1, LAYERS, DROPOUT).to(device).train()
     ddp = MeshDataParallel(model) if dist_on else None
-    opt = torch.optim.AdamW(model.parameters(), lr=LR, weight_decay=WD, fused=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=LR, weight_decay=WD, fused=True, capturable=True)
     crit = MaskedMSELoss()
 
     def train_step(b, read_loss=False, return_loss=False):
@@ -349,8 +350,21 @@ def main():
         loss_pin = torch.empty(steps, dtype=torch.float32).pin_memory()
         loss_evs, loss_vals = [], []
 
+        use_graph = not dist_on and not args.no_graph
+        if use_graph:
+            from deep_fem_uav_wing.gnn.graphed import GraphedTrainStep
+
+            gstep = GraphedTrainStep(model, crit, opt, eager_steps=2)
+            for _ in range(4):  # first calls of the shape run eagerly, then the step is captured
+                b = next(it)
+                gstep(b.x, b.edge_index, b.y, b.loss_mask)
+
         def e2e_step(i):
-            loss = train_step(next(it), return_loss=True)
+            if use_graph:
+                b = next(it)
+                loss = gstep(b.x, b.edge_index, b.y, b.loss_mask)
+            else:
+                loss = train_step(next(it), return_loss=True)
             loss_pin[i:i + 1].copy_(loss.reshape(1).float(), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
@@ -365,9 +379,9 @@ def main():
         ms_e2e = timed_region(e2e_step, steps, dist_on, device)
         assert len(loss_vals) == steps and all(np.isfinite(loss_vals)), "e2e losses were not all read back"
         e2e = {"value": BATCH * steps * world / (ms_e2e * 1e-3), "unit": "meshes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e / steps,
+               "ms_per_step": ms_e2e / steps, "cuda_graph": bool(use_graph),
                "path": "DataLoader(pinned host Data, device=cuda) -> H2D on a copy stream (1 batch prefetch) -> GraphSAGEModel(x, edge_index, batch) "
-                       "incl. on-device CSR build -> MaskedMSELoss -> backward -> AdamW -> loss copied to pinned host memory and read "
+                       "incl. on-device CSR build -> MaskedMSELoss -> backward -> AdamW (one CUDA graph per batch shape when single-GPU) -> loss copied to pinned host memory and read "
                        "(every step, one step behind the launch front)"}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------

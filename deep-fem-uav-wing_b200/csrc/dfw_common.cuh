@@ -94,6 +94,10 @@ __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
     z = z ^ (z >> 31);
     return static_cast<uint32_t>(z >> 32);
 }
+// seed given by value, or (DFW_EP_SEED_IS_PTR) read from device memory at kernel time
+__device__ __forceinline__ uint64_t resolve_seed(uint64_t seed, int flags) {
+    return (flags & DFW_EP_SEED_IS_PTR) ? *reinterpret_cast<const uint64_t*>(static_cast<uintptr_t>(seed)) : seed;
+}
 // keep iff bits >= threshold, threshold = p * 2^32
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
     double t = static_cast<double>(p) * 4294967296.0;

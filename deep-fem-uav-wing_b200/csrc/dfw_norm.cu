@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
     const int H = p.H;
     const float invH = 1.f / (float)H;
     const bool ln = p.flags & DFW_EP_LAYERNORM, relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
+    const uint64_t seed_v = drop ? resolve_seed(p.seed, p.flags) : 0ull;
     const T* gout = (const T*)p.g_out;
     const T* pre = (const T*)p.pre_out;
     const T* act = (const T*)p.act;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
                 if (drop) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        keep[j] = dropout_bits(p.seed, (uint64_t)off + j) >= p.drop_thr ? p.drop_scale : 0.f;
+                        keep[j] = dropout_bits(seed_v, (uint64_t)off + j) >= p.drop_thr ? p.drop_scale : 0.f;
                 }
                 if (ln) {
 #pragma unroll

@@ -86,6 +86,7 @@ class GraphSAGEModel(nn.Module):
         self.num_layers = num_layers
         self.dropout = dropout
         self.compute_dtype = torch.float32
+        self.device_seeds = None  # int64 CUDA tensor [num_layers + 1]: dropout seeds read by the kernels (CUDA-graph mode)
 
         self.encoder = nn.Sequential(
             nn.Linear(in_channels, 64), nn.ReLU(), nn.Linear(64, hidden_channels), nn.ReLU()
@@ -115,7 +116,13 @@ class GraphSAGEModel(nn.Module):
         out_dtype = x.dtype
         h = ops.cast_ad(x, cd)
         p = float(self.dropout) if self.training else 0.0
-        seed = _next_seed() if p > 0.0 else 0
+        if p > 0.0 and self.device_seeds is not None:  # seeds live on the device (see gnn/graphed.py)
+            layer_seed = [self.device_seeds[i:i + 1] for i in range(self.num_layers)]
+            dec_seed = self.device_seeds[self.num_layers:self.num_layers + 1]
+        else:
+            seed = _next_seed() if p > 0.0 else 0
+            layer_seed = [seed + 0x632BE5AB * (i + 1) for i in range(self.num_layers)]
+            dec_seed = seed + 0x7F4A7C15
 
         enc0, enc2 = self.encoder[0], self.encoder[2]
         h = ops.LinearFn.apply(h, enc0.weight, enc0.bias, True, 0.0, 0)
@@ -123,13 +130,13 @@ class GraphSAGEModel(nn.Module):
 
         for i, (conv, norm) in enumerate(zip(self.convs, self.norms)):
             h = ops.SageConvFn.apply(h, conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight, norm.weight, norm.bias, graph,
-                                     float(norm.eps), p, seed + 0x632BE5AB * (i + 1), True)
+                                     float(norm.eps), p, layer_seed[i], True)
 
         dec0, dec3 = self.decoder[0], self.decoder[3]
         if self.out_channels == 1:
-            out = ops.DecoderTailFn.apply(h, dec0.weight, dec0.bias, dec3.weight, dec3.bias, p, seed + 0x7F4A7C15)
+            out = ops.DecoderTailFn.apply(h, dec0.weight, dec0.bias, dec3.weight, dec3.bias, p, dec_seed)
         else:
-            hid = ops.LinearFn.apply(h, dec0.weight, dec0.bias, True, p, seed + 0x7F4A7C15)
+            hid = ops.LinearFn.apply(h, dec0.weight, dec0.bias, True, p, dec_seed)
             out = ops.LinearFn.apply(hid, dec3.weight, dec3.bias, False, 0.0, 0)
         return ops.cast_ad(out, out_dtype)
 

@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 import torch
 
 from . import _cabi
-from ._cabi import DFW_BF16, DFW_F32, EP_DROPOUT, EP_LAYERNORM, EP_RELU, EP_RESIDUAL, check, lib
+from ._cabi import DFW_BF16, DFW_F32, EP_DROPOUT, EP_LAYERNORM, EP_RELU, EP_RESIDUAL, EP_SEED_IS_PTR, check, lib
 
 _DTYPES = {torch.float32: DFW_F32, torch.bfloat16: DFW_BF16}
 LAUNCH_COUNTER = {"kernels": 0}  # kernels launched through the C ABI (bench.py's gpu_launches)
@@ -85,6 +85,14 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
             f"{what} must be a CUDA tensor (got device {t.device}): deep_fem_uav_wing.gnn is the B200-native "
             "implementation and has no CPU fallback."
         )
+
+
+def _seed_arg(seed):
+    """Dropout seed by value (python int) or by reference (1-element int64 CUDA tensor, read by the kernel at run
+    time - what a captured CUDA graph needs to draw a fresh mask on every replay)."""
+    if isinstance(seed, torch.Tensor):
+        return seed.data_ptr(), EP_SEED_IS_PTR
+    return int(seed) & 0xFFFFFFFFFFFFFFFF, 0
 
 
 def _f32(t):
@@ -232,8 +240,9 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=Fals
         flags |= EP_LAYERNORM
     if residual is not None:
         flags |= EP_RESIDUAL
+    seed_v, seed_flag = _seed_arg(seed)
     if dropout_p > 0.0:
-        flags |= EP_DROPOUT
+        flags |= EP_DROPOUT | seed_flag
     out = torch.empty(N, Hout, dtype=dt, device=dev) if want_out else None
     pre = torch.empty(N, Hout, dtype=dt, device=dev) if save_pre else None
     stats = torch.empty(N, 2, dtype=torch.float32, device=dev) if (save_pre and ln is not None) else None
@@ -249,7 +258,7 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=Fals
         check(lib.dfw_linear_fwd(
             a1.data_ptr(), w1.data_ptr(), k1, _ptr(a2), _ptr(w2), 0 if a2 is None else a2.shape[1], _ptr(bias),
             _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(eps), _ptr(residual),
-            float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), _ptr(pre), _ptr(stats),
+            float(dropout_p), seed_v, _ptr(out), _ptr(pre), _ptr(stats),
             _ptr(rowdot[0]) if rowdot is not None else None, _ptr(rowdot[1]) if rowdot is not None else None, _ptr(rd_out),
             N, Hout, flags, _dt(a1), ws.data_ptr(), ws_bytes, _stream(a1)))
     LAUNCH_COUNTER["kernels"] += 1
@@ -259,7 +268,8 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=Fals
 def epilogue_bwd(g_out, N, Hout, dtype_like, *, g_rowdot=None, rowdot_w=None, pre=None, stats=None, act=None, ln=None,
                  relu=False, dropout_p=0.0, seed=0, want_bias_grad=False):
     dev = dtype_like.device
-    flags = (EP_RELU if relu else 0) | (EP_LAYERNORM if ln is not None else 0) | (EP_DROPOUT if dropout_p > 0.0 else 0)
+    seed_v, seed_flag = _seed_arg(seed)
+    flags = (EP_RELU if relu else 0) | (EP_LAYERNORM if ln is not None else 0) | ((EP_DROPOUT | seed_flag) if dropout_p > 0.0 else 0)
     g_y = torch.empty(N, Hout, dtype=dtype_like.dtype, device=dev)
     dgamma = dbeta = d_rw = d_rb = None
     if ln is not None:
@@ -277,7 +287,7 @@ def epilogue_bwd(g_out, N, Hout, dtype_like, *, g_rowdot=None, rowdot_w=None, pr
         check(lib.dfw_epilogue_bwd(
             _ptr(g_out), _ptr(g_rowdot), _ptr(rowdot_w), _ptr(pre), _ptr(stats), _ptr(act),
             _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(dropout_p),
-            int(seed) & 0xFFFFFFFFFFFFFFFF, g_y.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(d_rw), _ptr(d_rb), _ptr(d_bias), N, Hout, flags,
+            seed_v, g_y.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(d_rw), _ptr(d_rb), _ptr(d_bias), N, Hout, flags,
             _DTYPES[dtype_like.dtype], ws.data_ptr(), ws_bytes, _stream(dtype_like)))
     LAUNCH_COUNTER["kernels"] += 2 if (ln is not None or g_rowdot is not None or want_bias_grad) else 1
     return g_y, dgamma, dbeta, d_rw, d_rb, d_bias

@@ -39,7 +39,9 @@ enum {
     DFW_EP_RELU = 1,      /* ReLU after (optional) LayerNorm                    model.py:92, :54,:56,:69 */
     DFW_EP_LAYERNORM = 2, /* row LayerNorm(eps, gamma, beta) before ReLU        model.py:64,91          */
     DFW_EP_RESIDUAL = 4,  /* out = residual + epilogue(...)                     model.py:95             */
-    DFW_EP_DROPOUT = 8    /* inverted dropout (train only)                      model.py:93, :70        */
+    DFW_EP_DROPOUT = 8,   /* inverted dropout (train only)                      model.py:93, :70        */
+    DFW_EP_SEED_IS_PTR = 16 /* `seed` is a DEVICE pointer to one uint64 (read by the kernel): lets a captured CUDA graph
+                             draw a fresh dropout mask on every replay */
 };
 
 const char* dfw_last_error(void);
