@@ -34,6 +34,10 @@ __device__ __forceinline__ int ldg_stream_s32(const int* p) {
     return r;
 }
 
+__device__ __forceinline__ void stg_v4(void* p, const uint4& v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // acc (fp32) += one 16-byte vector of T
 template <typename T>
 struct Acc;
@@ -76,17 +80,28 @@ struct Acc<__nv_bfloat16> {
     }
 };
 
-constexpr int kAggThreads = 1024;
 
 // Persistent: one 32-warp CTA per SM.  Rows are cut into CHUNKS of 32 row-blocks; chunk k belongs to CTA
 // k mod gridDim.x and a CTA's warps take the blocks of its chunks in order from a CTA-local counter.  So
-//  * inside an SM, ~32*R neighbouring rows are in flight together: the overlapping neighbourhoods of nearby
-//    rows are served by L1 (mesh numberings are banded: a source row is requested by several nearby
-//    destination rows) - L1 hit rate 15 % -> 57 % on the 2M-node lattice;
+//  * inside an SM, ~32*R neighbouring rows are in flight together; a warp walks R consecutive rows, whose
+//    overlapping neighbourhoods hit L1 (34 % on the 2M-node lattice = exactly the row-to-next-row overlap: with
+//    128 KB of gathers in flight per SM, L1 lines do not live long enough for reuse between warps);
 //  * across the chip, all SMs advance through the node array as ONE wavefront (148 chunks wide), so the
-//    longer-range reuse (neighbouring lattice planes) stays inside the 126 MB L2 and DRAM sees each row once.
-// (A contiguous band per SM gives the first property but loses the second: DRAM reads tripled.)
-template <typename T, int LANES, int VPL>
+//    longer-range reuse (neighbouring lattice planes) stays inside the 126 MB L2 and DRAM sees each row once
+//    (ncu: DRAM traffic 2.2 GB = A_min).  (A contiguous band per SM loses this: DRAM reads tripled.)
+//
+// Inner loop, shaped by the ncu captures under profiles/ (r01):
+//  * v1 spent 31 warp instructions per edge (79 % issue utilisation on a bf16 row).  Now an edge costs one
+//    IMAD.WIDE (row address = column * row_bytes + opaque lane base; the other 16-byte vectors of the row are
+//    immediate offsets when EXACT), the LDG.128s and the adds; column indices come kU at a time from ONE
+//    broadcast LDS.128 of a shared-memory window (no SHFL per edge); row ends are tested once per batch of kU
+//    edges and per edge only in batches holding one: 20 instructions per edge, 998 -> 710 us on cfg4.
+//  * What bounds cfg4 now is the L2 -> SM fabric: 9.3 GB of L1 misses in 0.71 ms = 13 TB/s, the full-chip LTS
+//    cap (~6300 B/clk).  Only more on-SM reuse (explicit de-duplication of a chunk's neighbours in shared
+//    memory) can lift it further.
+//  * PIPE (batch b+1 in flight while batch b is added) is kept as a template switch: it helps at 16 warps but
+//    32 warps x one batch hide the per-block prologue (rowptr -> col -> rows) better (745 vs 956 us).
+template <typename T, int LANES, int VPL, bool HAS_ADD, bool EXACT, int kAggThreads, int KUDIV, bool PIPE>
 __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                               const float* __restrict__ row_scale, const T* __restrict__ x,
                                                               const T* __restrict__ addend, T* __restrict__ out, int64_t N,
@@ -94,8 +109,12 @@ __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __r
     using V = Vec16<T>;
     constexpr int EPV = V::N;
     constexpr int GROUPS = 32 / LANES;
-    constexpr int kU = VPL >= 4 ? 2 : (VPL == 2 ? 4 : 8);  // source rows in flight per group (8 x 16 B per lane)
+    constexpr int kU0 = VPL >= 4 ? 2 : (VPL == 2 ? 4 : 8);  // source rows per batch (8 x 16 B per lane), two batches in flight
+    constexpr int kU1 = kU0 / KUDIV < 2 ? 2 : kU0 / KUDIV;
+    constexpr int kU = kU1 < LANES ? kU1 : LANES;
+    static_assert(LANES % kU == 0, "a column window holds whole batches");
     __shared__ int s_next;
+    __shared__ __align__(16) int s_cols[kAggThreads / 32][2][32];
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
     const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane / LANES * LANES));
@@ -104,17 +123,26 @@ __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __r
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
     // Lanes past the end of a row (only when nvec < LANES*VPL) load a clamped, valid vector and never
-    // store: every load below is UNCONDITIONAL, so the compiler keeps kU independent requests in flight.
+    // store: every load below is UNCONDITIONAL, so the compiler keeps the requests of a batch in flight together.
+    const uint32_t row_bytes = (uint32_t)nvec * 16u;
     bool vec_ok[VPL];
-    int voff[VPL];
+    uint32_t dlt[VPL];  // byte offset of vector v relative to vector 0 of this lane
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-        vec_ok[v] = (sub + v * LANES) < nvec;
-        voff[v] = min(sub + v * LANES, nvec - 1);
+        vec_ok[v] = EXACT || (sub + v * LANES) < nvec;
+        dlt[v] = EXACT ? (uint32_t)(v * LANES * 16) : (uint32_t)(min(sub + v * LANES, nvec - 1) - min(sub, nvec - 1)) * 16u;
     }
-    const uint4* xv = reinterpret_cast<const uint4*>(x);
-    const uint4* av = addend ? reinterpret_cast<const uint4*>(addend) : nullptr;
-    uint4* ov = reinterpret_cast<uint4*>(out);
+    const uint32_t lane_off = (uint32_t)min(sub, nvec - 1) * 16u;
+    // lane base pointers, made opaque so that a row address is ONE IMAD.WIDE (c * row_bytes + base) instead of
+    // the compiler's re-association (c * row_bytes + lane_off) + x  (IMAD.WIDE + IADD3 + IADD3.X)
+    uint64_t xl_ = reinterpret_cast<uint64_t>(x) + lane_off;
+    uint64_t al_ = HAS_ADD ? reinterpret_cast<uint64_t>(addend) + lane_off : 0;
+    uint64_t ol_ = reinterpret_cast<uint64_t>(out) + lane_off;
+    asm volatile("" : "+l"(xl_), "+l"(al_), "+l"(ol_));
+    const char* xl = reinterpret_cast<const char*>(xl_);
+    const char* al = reinterpret_cast<const char*>(al_);
+    char* ol = reinterpret_cast<char*>(ol_);
+    int* const wcols = &s_cols[threadIdx.x >> 5][0][lane - sub];  // this group's slice of the two column windows
 
   for (;;) {
     int blk = 0;
@@ -138,88 +166,166 @@ __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __r
     for (int v = 0; v < VPL; ++v) acc[v].zero();
     uint4 ad[VPL];
     int cur = 0;                                          // current row inside the block
-    int cur_end = __shfl_sync(gmask, rp, 1, LANES);       // its end edge
+    int cur_end = __shfl_sync(gmask, rp, 1, LANES);       // its end edge; INT_MAX once every row is written
     auto fetch_addend = [&](int r) {
-        if (av) {
+        if (HAS_ADD) {
+            const char* p = al + (uint64_t)(r0 + r) * row_bytes;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) ad[v] = ldg_nc_v4(av + (r0 + r) * nvec + voff[v]);
+            for (int v = 0; v < VPL; ++v) ad[v] = ldg_nc_v4(reinterpret_cast<const uint4*>(p + dlt[v]));
         }
     };
     auto flush = [&]() {  // write row `cur`, start the next one
-        const int64_t row = r0 + cur;
         const float sc = __shfl_sync(gmask, rsc, cur, LANES);
+        char* po = ol + (uint64_t)(r0 + cur) * row_bytes;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-            if (vec_ok[v]) {
-                float f[EPV];
-                acc[v].get(f);
-                if (av) {
-                    V a;
-                    a.v = *reinterpret_cast<decltype(a.v)*>(&ad[v]);
-                    float g[EPV];
-                    a.to_float(g);
+            float f[EPV];
+            acc[v].get(f);
+            if (HAS_ADD) {
+                V a;
+                a.v = *reinterpret_cast<decltype(a.v)*>(&ad[v]);
+                float g[EPV];
+                a.to_float(g);
 #pragma unroll
-                    for (int i = 0; i < EPV; ++i) f[i] = fmaf(f[i], sc, g[i]);
-                } else {
+                for (int i = 0; i < EPV; ++i) f[i] = fmaf(f[i], sc, g[i]);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < EPV; ++i) f[i] *= sc;
-                }
-                V o;
-                o.from_float(f);
-                ov[row * nvec + voff[v]] = *reinterpret_cast<uint4*>(&o.v);
+                for (int i = 0; i < EPV; ++i) f[i] *= sc;
             }
+            V o;
+            o.from_float(f);
+            if (vec_ok[v]) stg_v4(po + dlt[v], *reinterpret_cast<uint4*>(&o.v));
             acc[v].zero();
         }
         ++cur;
         if (cur < nrows) {
             cur_end = __shfl_sync(gmask, rp, cur + 1, LANES);
             fetch_addend(cur);
+        } else {
+            cur_end = 0x7fffffff;  // the padding edges of the last batch fall into an accumulator nobody writes
         }
     };
     fetch_addend(0);
 
-    for (int eb = e_beg; eb < e_end; eb += LANES) {
-        const int n = min(LANES, e_end - eb);
-        // lanes past the end of the edge range repeat the last valid column (a harmless L1 hit)
-        const int mine = ldg_stream_s32(col + eb + min(sub, n - 1));
-        for (int j0 = 0; j0 < n; j0 += kU) {
+    const int ne = e_end - e_beg;
+    const int nbatch = (ne + kU - 1) / kU;
+    // lanes past the end of the edge range repeat the last valid column (a harmless L1 hit), so every slot of a
+    // window holds a loadable column and a batch needs no bounds checks
+    int mine = ne > 0 ? ldg_stream_s32(col + e_beg + min(sub, min(LANES, ne) - 1)) : 0;
+    // request the rows of batch b into `buf`; the first batch of a column window parks the window in shared memory
+    // and requests the next window's columns
+    auto issue = [&](uint4 (&buf)[kU][VPL], int b) {
+        const int j = b * kU;
+        const int within = j & (LANES - 1);
+        int* w = wcols + ((j / LANES) & 1) * 32;
+        if (within == 0) {
+            w[sub] = mine;
+            __syncwarp(gmask);
+            const int nxt = j + LANES;
+            if (nxt < ne) mine = ldg_stream_s32(col + e_beg + nxt + min(sub, min(LANES, ne - nxt) - 1));
+        }
+        uint32_t cb[kU];
+        if constexpr (kU == 8) {
+            const uint4 c0 = *reinterpret_cast<const uint4*>(w + within), c1 = *reinterpret_cast<const uint4*>(w + within + 4);
+            cb[0] = c0.x; cb[1] = c0.y; cb[2] = c0.z; cb[3] = c0.w; cb[4] = c1.x; cb[5] = c1.y; cb[6] = c1.z; cb[7] = c1.w;
+        } else if constexpr (kU == 4) {
+            const uint4 c0 = *reinterpret_cast<const uint4*>(w + within);
+            cb[0] = c0.x; cb[1] = c0.y; cb[2] = c0.z; cb[3] = c0.w;
+        } else {
+            const uint2 c0 = *reinterpret_cast<const uint2*>(w + within);
+            cb[0] = c0.x; cb[1] = c0.y;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const char* p = xl + (uint64_t)cb[u] * row_bytes;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_nc_v4(reinterpret_cast<const uint4*>(p + dlt[v]));
+        }
+    };
+    auto consume = [&](uint4 (&buf)[kU][VPL], int b) {
+        const int ebase = e_beg + b * kU;
+        if (cur_end - ebase >= kU) {  // whole batch inside the current row
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) acc[v].add(buf[u][v]);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                while (ebase + u == cur_end) flush();  // group-uniform; also steps over empty rows
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) acc[v].add(buf[u][v]);
+            }
+        }
+    };
+    if constexpr (PIPE) {
+        uint4 bufA[kU][VPL], bufB[kU][VPL];
+        if (nbatch > 0) issue(bufA, 0);
+        for (int b = 0; b < nbatch; b += 2) {
+            if (b + 1 < nbatch) issue(bufB, b + 1);
+            consume(bufA, b);
+            if (b + 1 >= nbatch) break;
+            if (b + 2 < nbatch) issue(bufA, b + 2);
+            consume(bufB, b + 1);
+        }
+    } else {
+        for (int b = 0; b < nbatch; ++b) {
             uint4 buf[kU][VPL];
-            const int m = min(kU, n - j0);
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int c = __shfl_sync(gmask, mine, min(j0 + u, n - 1), LANES);
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_nc_v4(xv + (int64_t)c * nvec + voff[v]);
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                if (u < m) {
-                    const int e = eb + j0 + u;
-                    while (e == cur_end) flush();  // group-uniform; also steps over empty rows
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) acc[v].add(buf[u][v]);
-                }
-            }
+            issue(buf, b);
+            consume(buf, b);
         }
     }
     while (cur < nrows) flush();  // last row and trailing empty rows
   }
 }
 
+// rows per group: about a dozen rows / <= 192 edges per group amortise the rowptr/col round trips of a block (the
+// dependent prologue of every block is what the 32 warps have to hide); among the candidates take the one whose
+// chunk count fills whole waves of 148 CTAs best (a 200k-row batch is only ~4 waves: 3.25 waves cost 4)
+inline int pick_rows_per_group(int64_t N, int64_t E, int lanes, int groups, int threads) {
+    const double deg = N > 0 ? (double)E / (double)N : 0.0;
+    int hi = (int)(192.0 / (deg + 1.0));
+    hi = std::max(1, std::min(hi, std::min(12, lanes - 1)));
+    const int lo = std::max(1, (hi * 2 + 2) / 3);
+    int best = hi;
+    double best_eff = -1.0;
+    for (int R = hi; R >= lo; --R) {
+        const int64_t chunk_rows = (int64_t)R * groups * (threads / 32);
+        const int64_t chunks = (N + chunk_rows - 1) / chunk_rows;
+        const int64_t waves = (chunks + kNumSMs - 1) / kNumSMs;
+        const double eff = (double)N / ((double)waves * kNumSMs * (double)chunk_rows);
+        if (eff > best_eff + 0.02) {  // prefer larger R unless a smaller one is clearly better balanced
+            best_eff = eff;
+            best = R;
+        }
+    }
+    return best;
+}
+
+// 32 warps x one batch of kU rows in flight beat 16 warps x two software-pipelined batches (cfg4: 745 vs 956 us)
+// and 32 warps x two half batches (750 us): thread-level parallelism hides the per-block prologue best.
+constexpr int kAggThreads = 1024;
+
 template <typename T, int LANES, int VPL>
 int launch(const int32_t* rowptr, const int32_t* col, const float* row_scale, const void* x, const void* addend,
            void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
     constexpr int GROUPS = 32 / LANES;
-    // rows per group: aim at ~64 edges per group so that rowptr/col latency is amortised, keep R < LANES
-    const double deg = N > 0 ? (double)E / (double)N : 0.0;
-    int R = (int)(96.0 / (deg + 1.0));
-    R = std::max(1, std::min(R, std::min(16, LANES - 1)));
+    const int R = pick_rows_per_group(N, E, LANES, GROUPS, kAggThreads);
     const int64_t chunk_rows = (int64_t)R * GROUPS * (kAggThreads / 32);
     const int64_t chunks = (N + chunk_rows - 1) / chunk_rows;
     const int64_t blocks = std::min<int64_t>(chunks, kNumSMs);
     if (blocks == 0) return 0;
-    k_aggregate<T, LANES, VPL><<<(unsigned)blocks, kAggThreads, 0, s>>>(rowptr, col, row_scale, (const T*)x, (const T*)addend,
-                                                                        (T*)out, N, nvec, R);
+    const bool exact = nvec == LANES * VPL;
+#define DFW_AGG_GO(A, X)                                                                                                       \
+    k_aggregate<T, LANES, VPL, A, X, kAggThreads, 1, false><<<(unsigned)blocks, kAggThreads, 0, s>>>(rowptr, col, row_scale, (const T*)x, \
+                                                                                                     (const T*)addend, (T*)out, N, nvec, R)
+    if (exact) {
+        if (addend) DFW_AGG_GO(true, true); else DFW_AGG_GO(false, true);
+    } else {
+        if (addend) DFW_AGG_GO(true, false); else DFW_AGG_GO(false, false);
+    }
+#undef DFW_AGG_GO
     DFW_LAUNCH_CHECK();
     return 0;
 }
