@@ -330,7 +330,7 @@ def main():
                 "note": "algorithmic bytes per launch (DESIGN.md) / mean CUDA-event duration; every kernel of the step is listed under `kernels`"}
 
     # ---- arm 2: end to end through the public API from pinned host memory ----------------------
-    e2e = None
+    e2e, gstep = None, None
     if not args.no_e2e:
         host_loader = DataLoader(datas, batch_size=BATCH, shuffle=False, device=device)
         h2d = sum(int(getattr(datas[j], k).numel() * getattr(datas[j], k).element_size()) for j in range(BATCH)
@@ -350,11 +350,11 @@ def main():
         loss_pin = torch.empty(steps, dtype=torch.float32).pin_memory()
         loss_evs, loss_vals = [], []
 
-        use_graph = not dist_on and not args.no_graph
+        use_graph = not args.no_graph
         if use_graph:
             from deep_fem_uav_wing.gnn.graphed import GraphedTrainStep
 
-            gstep = GraphedTrainStep(model, crit, opt, eager_steps=2)
+            gstep = GraphedTrainStep(model, crit, opt, eager_steps=2, ddp=ddp)
             for _ in range(4):  # first calls of the shape run eagerly, then the step is captured
                 b = next(it)
                 gstep(b.x, b.edge_index, b.y, b.loss_mask)
@@ -381,7 +381,7 @@ def main():
         e2e = {"value": BATCH * steps * world / (ms_e2e * 1e-3), "unit": "meshes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / steps, "cuda_graph": bool(use_graph),
                "path": "DataLoader(pinned host Data, device=cuda) -> H2D on a copy stream (1 batch prefetch) -> GraphSAGEModel(x, edge_index, batch) "
-                       "incl. on-device CSR build -> MaskedMSELoss -> backward -> AdamW (one CUDA graph per batch shape when single-GPU) -> loss copied to pinned host memory and read "
+                       "incl. on-device CSR build -> MaskedMSELoss -> backward -> AdamW (one CUDA graph per batch shape, gradient all-reduce captured with it) -> loss copied to pinned host memory and read "
                        "(every step, one step behind the launch front)"}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
@@ -403,8 +403,16 @@ def main():
         }
         emit(line)
     if dist_on:
+        # the captured steps hold NCCL work: release the graphs, agree that everybody is done, and leave without
+        # tearing the communicator down (destroying a communicator that graphs still reference can block)
+        gstep = None
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize(device)
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

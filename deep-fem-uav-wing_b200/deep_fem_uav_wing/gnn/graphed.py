@@ -10,6 +10,9 @@ pool) and replays it: per step the host only copies the batch into the static bu
 * The CSR build of ``edge_index`` is part of the graph (it depends on the batch).
 * Dropout: seeds live in a device tensor that the graph bumps before the forward, so every replay draws new masks.
 * Optimizer: must be created with ``capturable=True`` (step counter on the device).
+* Data parallel: pass the ``MeshDataParallel`` wrapper as ``ddp``; the masked-count all-reduce, the bucketed gradient
+  all-reduces (launched from the autograd hooks while the rest of the backward is still being recorded) and the wait
+  before the optimizer are captured with the step, so a replay costs one launch per rank, NCCL included.
 """
 from __future__ import annotations
 
@@ -19,8 +22,8 @@ from . import ops
 
 
 class GraphedTrainStep:
-    def __init__(self, model, criterion, optimizer, eager_steps: int = 3, max_graphs: int = 8):
-        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+    def __init__(self, model, criterion, optimizer, eager_steps: int = 3, max_graphs: int = 8, ddp=None):
+        self.model, self.criterion, self.optimizer, self.ddp = model, criterion, optimizer, ddp
         self.eager_steps, self.max_graphs = eager_steps, max_graphs
         self._seen: dict = {}
         self._graphs: dict = {}
@@ -31,13 +34,24 @@ class GraphedTrainStep:
             model.device_seeds = torch.randint(0, 2**62, (model.num_layers + 1,), generator=g, dtype=torch.int64).to(dev)
         self._pool = None
 
-    def _eager(self, x, edge_index, y, mask):
-        self.optimizer.zero_grad(set_to_none=True)
+    def _step(self, x, edge_index, y, mask):
+        """One training step (``train_gnn.py:50-60``); runs eagerly or under capture."""
         self.model.device_seeds.add_(0x9E3779B97F4A7C15 & 0x3FFFFFFFFFFFFFFF)
+        if self.ddp is not None:
+            self.ddp.zero_grad()  # gradients are views of one flat buffer: zero in place (also inside the graph)
         loss = self.criterion(self.model(x, edge_index, None), y, mask)
-        loss.backward()
+        if self.ddp is not None:
+            self.ddp.scale_loss(loss, self.criterion.last_count).backward()
+            self.ddp.finish()
+        else:
+            loss.backward()
         self.optimizer.step()
         return loss.detach()
+
+    def _eager(self, x, edge_index, y, mask):
+        if self.ddp is None:
+            self.optimizer.zero_grad(set_to_none=True)
+        return self._step(x, edge_index, y, mask)
 
     def __call__(self, x, edge_index, y, mask):
         key = (int(x.shape[0]), int(edge_index.shape[1]), x.dtype)
@@ -63,14 +77,12 @@ class GraphedTrainStep:
         sx.copy_(x); se.copy_(edge_index); sy.copy_(y); sm.copy_(mask)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        if self.ddp is None:
+            self.optimizer.zero_grad(set_to_none=True)
         k0 = ops.LAUNCH_COUNTER["kernels"]
-        with torch.cuda.graph(g, pool=self._pool):
-            self.model.device_seeds.add_(0x9E3779B97F4A7C15 & 0x3FFFFFFFFFFFFFFF)
-            loss = self.criterion(self.model(sx, se, None), sy, sm)
-            loss.backward()
-            self.optimizer.step()
-            sloss = loss.detach()
+        # thread_local: the NCCL watchdog thread may poll events while this thread captures
+        with torch.cuda.graph(g, pool=self._pool, capture_error_mode="thread_local"):
+            sloss = self._step(sx, se, sy, sm)
         self.kernels_per_replay = ops.LAUNCH_COUNTER["kernels"] - k0
         if self._pool is None:
             self._pool = g.pool()
