@@ -85,15 +85,25 @@ __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 
-// Counter-based dropout RNG: keep-mask is a pure function of (seed, element index), so the
-// backward regenerates it instead of storing a mask.  splitmix64 finaliser.
-__device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
-    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return static_cast<uint32_t>(z >> 32);
+// Counter-based dropout RNG: the keep-mask is a pure function of (seed, row, column), so the backward regenerates
+// it instead of storing a mask.  Two levels, both the 32-bit "lowbias32" finaliser: a key per ROW (computed once by
+// the thread or warp that owns the row) and ~9 integer instructions per element.  (The first version hashed a
+// 64-bit element index with splitmix64: ~30 instructions per element, which made the thread-per-row epilogue of the
+// tensor-core linear and the LayerNorm backward ALU bound.)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x21f0aaadu;
+    x ^= x >> 15;
+    x *= 0x735a2d97u;
+    x ^= x >> 15;
+    return x;
 }
+__device__ __forceinline__ uint32_t dropout_row_key(uint64_t seed, uint64_t row) {
+    uint32_t k = mix32(static_cast<uint32_t>(row) ^ static_cast<uint32_t>(seed));
+    k += static_cast<uint32_t>(row >> 32) * 0x85EBCA6Bu + static_cast<uint32_t>(seed >> 32);
+    return mix32(k);
+}
+__device__ __forceinline__ uint32_t dropout_bits(uint32_t row_key, uint32_t col) { return mix32(row_key + col * 0x9E3779B9u); }
 // seed given by value, or (DFW_EP_SEED_IS_PTR) read from device memory at kernel time
 __device__ __forceinline__ uint64_t resolve_seed(uint64_t seed, int flags) {
     return (flags & DFW_EP_SEED_IS_PTR) ? *reinterpret_cast<const uint64_t*>(static_cast<uintptr_t>(seed)) : seed;

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kThreads) k_linear(const LinArgs p) {
 #pragma unroll
                 for (int j = 0; j < TN; ++j) {
                     const int c = tile_index<TN, BN / 2>(tx, j);
-                    const uint32_t bits = dropout_bits(resolve_seed(p.seed, p.flags), (uint64_t)r * (uint64_t)H + (uint64_t)c);
+                    const uint32_t bits = dropout_bits(dropout_row_key(resolve_seed(p.seed, p.flags), (uint64_t)r), (uint32_t)c);
                     v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
                 }
             }

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
         const bool ln = p.flags & DFW_EP_LAYERNORM;
         const bool relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
-        const uint64_t seed_v = drop ? resolve_seed(p.seed, p.flags) : 0ull;
+        const uint32_t row_key = drop ? dropout_row_key(resolve_seed(p.seed, p.flags), (uint64_t)row) : 0u;
         const float4* bias4 = reinterpret_cast<const float4*>(cvec);
         const float4* gam4 = reinterpret_cast<const float4*>(cvec + 256);
         const float4* bet4 = reinterpret_cast<const float4*>(cvec + 512);
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 if (drop) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const uint32_t bits = dropout_bits(seed_v, (uint64_t)row * (uint64_t)H + (uint64_t)(c0 + j));
+                        const uint32_t bits = dropout_bits(row_key, (uint32_t)(c0 + j));
                         v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
                     }
                 }

@@ -144,9 +144,10 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
                 }
                 float keep[4] = {1.f, 1.f, 1.f, 1.f};
                 if (drop) {
+                    const uint32_t row_key = dropout_row_key(seed_v, (uint64_t)row);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        keep[j] = dropout_bits(seed_v, (uint64_t)off + j) >= p.drop_thr ? p.drop_scale : 0.f;
+                        keep[j] = dropout_bits(row_key, (uint32_t)((lane + v * 32) * 4 + j)) >= p.drop_thr ? p.drop_scale : 0.f;
                 }
                 if (ln) {
 #pragma unroll
