@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
     const int mb_valid = min(NB, (p.Hout - ti * kDwTile + EPB - 1) / EPB);
     const int nb_valid = min(NB, (p.k[which] - tj * kDwTile + EPB - 1) / EPB);
     const int n_cols = nb_valid * EPB;
+    const bool stacked = TF32 && nb_valid == NB;  // see the MMA issuer
     if (mb_valid < NB) {
         for (int s = 0; s < p.stages; ++s) {
             uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * STAGE + G_HI + mb_valid * BOX);
@@ -149,6 +150,11 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
             int stage = 0;
             uint32_t phase = 0, accumulate = 0;
             uint32_t acc_main[2] = {0u, 0u}, acc_cross = 0u;  // fp32: two hi*hi accumulators + one for the cross terms
+            // full-width tiles: a_lo sits right behind a_hi (same block pitch), so ONE N = 256 instruction yields
+            // g_hi.a_hi (main) and g_hi.a_lo (cross) - two instructions per k-step instead of three (the MMA issue
+            // rate, ~140 clk per instruction whatever N, and the operand reads bound this kernel).  TMEM columns:
+            // [main0 | cross0 | main1 | cross1], k-steps alternate between the two pairs.
+            const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * kDwTile) >> 3) << 17);
             int kstep = 0;
             for (int it = 0; it < nsteps; ++it) {
                 mbar_wait(TF32 ? &conv[stage] : &full[stage], phase);
@@ -163,10 +169,15 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
                         const uint64_t g_lo = make_desc_mn<TF32>(st + G_LO + koff, BOX);
                         const uint64_t a_lo = make_desc_mn<TF32>(st + A_LO + koff, BOX);
                         const int m = kstep & 1;
-                        umma<TF32>(tmem_base + 2 * kDwTile, g_lo, a_hi, idesc, acc_cross);
-                        umma<TF32>(tmem_base + 2 * kDwTile, g_hi, a_lo, idesc, 1u);
-                        umma<TF32>(tmem_base + m * kDwTile, g_hi, a_hi, idesc, acc_main[m]);
-                        acc_cross = 1u;
+                        if (stacked) {
+                            umma<TF32>(tmem_base + m * 2 * kDwTile, g_hi, a_hi, idesc2, acc_main[m]);
+                            umma<TF32>(tmem_base + m * 2 * kDwTile + kDwTile, g_lo, a_hi, idesc, 1u);
+                        } else {
+                            umma<TF32>(tmem_base + 2 * kDwTile, g_lo, a_hi, idesc, acc_cross);
+                            umma<TF32>(tmem_base + 2 * kDwTile, g_hi, a_lo, idesc, 1u);
+                            umma<TF32>(tmem_base + m * kDwTile, g_hi, a_hi, idesc, acc_main[m]);
+                            acc_cross = 1u;
+                        }
                         acc_main[m] = 1u;
                         ++kstep;
                     } else {
@@ -194,14 +205,7 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
 #pragma unroll
                     for (int i = 0; i < (int)(OPER / 16) / 128; ++i) {
                         const int idx = et + i * 128;
-                        const float4 a = hi[idx];
-                        float4 h, l;
-                        h.x = __uint_as_float(rna_tf32(a.x)); l.x = __uint_as_float(rna_tf32(a.x - h.x));
-                        h.y = __uint_as_float(rna_tf32(a.y)); l.y = __uint_as_float(rna_tf32(a.y - h.y));
-                        h.z = __uint_as_float(rna_tf32(a.z)); l.z = __uint_as_float(rna_tf32(a.z - h.z));
-                        h.w = __uint_as_float(rna_tf32(a.w)); l.w = __uint_as_float(rna_tf32(a.w - h.w));
-                        hi[idx] = h;
-                        lo[idx] = l;
+                        lo[idx] = tf32_lo(hi[idx]);
                     }
                 }
                 fence_proxy_async();
@@ -226,14 +230,23 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
                 tmem_ld32(t_row + c0, v);
                 if (TF32) {  // round-to-nearest sum of the accumulators (see tmem_combine)
                     float w[32];
-                    if (two_main) {
-                        tmem_ld32(t_row + kDwTile + c0, w);
+                    if (stacked) {  // [main0 | cross0 | main1 | cross1]; a stage is 4 k-steps, so both pairs exist
+#pragma unroll
+                        for (int a = 1; a < 4; ++a) {
+                            tmem_ld32(t_row + a * kDwTile + c0, w);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += w[j];
+                        }
+                    } else {
+                        if (two_main) {
+                            tmem_ld32(t_row + kDwTile + c0, w);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += w[j];
+                        }
+                        tmem_ld32(t_row + 2 * kDwTile + c0, w);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += w[j];
                     }
-                    tmem_ld32(t_row + 2 * kDwTile + c0, w);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += w[j];
                 }
 #pragma unroll
                 for (int g = 0; g < 8; ++g)

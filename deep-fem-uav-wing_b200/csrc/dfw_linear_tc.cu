@@ -15,7 +15,8 @@
 //              In fp32 mode the same warps first act as CONVERTERS (see below).
 //   bf16 : kind::f16, operands straight from TMA.
 //   fp32 : 3xTF32 error-compensated split (kind::tf32): a = a_hi + a_lo, w = w_hi + w_lo with
-//          x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi);  D += a_lo.w_hi + a_hi.w_lo + a_hi.w_hi.
+//          x_hi = tf32(x), x_lo = tf32(x - x_hi);  D += a_lo.w_hi + a_hi.w_lo + a_hi.w_hi.  (weights: round to
+//          nearest, pre-split; activations: the hardware's own truncation, see tf32_lo)
 //          Per-element error ~2^-22, so results stay inside the 1e-5 fp32 parity bound where a single
 //          TF32 pass (2^-11) would not.  Weights are pre-split by a tiny kernel; the activation split is
 //          done in shared memory, in place, by the converter warps between the TMA and the MMA.
@@ -232,14 +233,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < (kTileM * CB / 16) / 128; ++i) {  // position-preserving: swizzle-agnostic
                     const int idx = et + i * 128;
-                    const float4 a = hi[idx];
-                    float4 h, l;
-                    h.x = __uint_as_float(rna_tf32(a.x)); l.x = __uint_as_float(rna_tf32(a.x - h.x));
-                    h.y = __uint_as_float(rna_tf32(a.y)); l.y = __uint_as_float(rna_tf32(a.y - h.y));
-                    h.z = __uint_as_float(rna_tf32(a.z)); l.z = __uint_as_float(rna_tf32(a.z - h.z));
-                    h.w = __uint_as_float(rna_tf32(a.w)); l.w = __uint_as_float(rna_tf32(a.w - h.w));
-                    hi[idx] = h;
-                    lo[idx] = l;
+                    lo[idx] = tf32_lo(hi[idx]);
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
                 mbar_arrive(&conv[stage]);

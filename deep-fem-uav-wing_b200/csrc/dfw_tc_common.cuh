@@ -136,6 +136,19 @@ __device__ __forceinline__ void fence_tc_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void fence_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Low half of the 3xTF32 split of an ACTIVATION.  The tensor core reads an fp32 word as tf32 by ignoring the low 13
+// mantissa bits, so the raw tile already IS a_hi = trunc_tf32(a): only a_lo = a - a_hi has to be written (exact in
+// fp32; its own truncation to tf32 leaves a relative error <= 2^-21).  Saves the converter warps a third of their
+// shared-memory traffic and the cvt.rna instructions (the converters' LDS/STS were 54 % of the L1 data pipe in dW).
+__device__ __forceinline__ float4 tf32_lo(const float4& a) {
+    float4 l;
+    l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xffffe000u);
+    l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xffffe000u);
+    l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xffffe000u);
+    l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xffffe000u);
+    return l;
+}
+
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

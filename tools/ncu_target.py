@@ -21,10 +21,18 @@ if what.startswith("linear"):
     b = torch.randn(H, device="cuda")
     g, be = torch.ones(H, device="cuda"), torch.zeros(H, device="cuda")
     for _ in range(3):
-        ops.linear_fwd(agg, w, x, w, bias=b, ln=(g, be), relu=True, residual=x, save_pre=("train" in what))
+        ops.linear_fwd(agg, w, x, w, bias=b, ln=(g, be), relu=True, residual=x, save_pre=("train" in what), dropout_p=0.1 if "train" in what else 0.0, seed=7)
     if "dx" in what:
         for _ in range(3):
             ops.linear_bwd_input(x, w, row_scale=b.new_ones(n))
+    if "dw" in what:
+        for _ in range(3):
+            ops.linear_bwd_weight(x, agg, x, want_bias=False)
+    if "epi" in what:
+        pre = torch.randn(n, H, device="cuda").to(dt)
+        stats = torch.rand(n, 2, device="cuda") + 0.5
+        for _ in range(3):
+            ops.epilogue_bwd(x, n, H, x, pre=pre, stats=stats, ln=(g, be), relu=True, dropout_p=0.1, seed=7, want_bias_grad=True)
 elif what.startswith("agg"):
     if "cfg4" in what:
         mesh = synth.tet_lattice_wing(2_000_000, seed=42, node_order="random" if "random" in what else "native", shuffle_edges=False)
