@@ -25,6 +25,7 @@
 
 #include <algorithm>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "dfw_common.cuh"
@@ -74,6 +75,20 @@ __host__ __device__ inline Smem carve(bool tf32, int Npad, int stages, int out_b
     return s;
 }
 
+#ifdef DFW_TC_PROBE
+__device__ long long* g_probe = nullptr;  // [64] stamps of one mid-grid CTA (tools/tc_timeline.py)
+__device__ __forceinline__ void probe(int slot) {
+    if (g_probe && blockIdx.x == gridDim.x / 2) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_probe[slot] = t;
+    }
+}
+#define PROBE(slot) probe(slot)
+#else
+#define PROBE(slot)
+#endif
+
 template <typename T, bool TF32>
 __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ Maps maps, const Args p) {
     constexpr int EPC = kChunkBytes / (int)sizeof(T);  // elements (columns) per 128-byte epilogue box: 32 fp32 / 64 bf16
@@ -96,8 +111,19 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m_base = (int64_t)blockIdx.x * kTileM;
+    const int64_t m_base = (int64_t)blockIdx.x * kTileM;  // CTAs padding the grid to whole clusters own an empty tile
     const int total_chunks = p.chunks[0] + p.chunks[1];
+    // Thread-block cluster: every CTA needs the SAME weight chunks, and at K*Hout*(4+4) bytes per 128-row tile they
+    // are two thirds of what a CTA pulls through the L2 fabric (ncu r01: 1.24 GB of L2 traffic per launch, 8.8 TB/s
+    // of a ~13 TB/s cap, for 0.4 GB of DRAM traffic).  So CTA 0 of the cluster fetches each weight chunk ONCE and
+    // multicasts it to all peers; every CTA loads its own activation rows.  A stage is refilled only when every CTA
+    // of the cluster has retired the MMAs that read it (the commits are multicast to every peer's `empty` barrier).
+    // MEASURED (r01, cfg2 fwd, L2 flushed): cluster 1 / 2 / 4 = 146 / 155 / 159 us - the lock-step between the CTAs costs
+    // more than the L2 reads save, because a tile is bound by the round trip of its few smem stages and by the
+    // tensor pipe (64 MMAs x ~140 clk per tile, shared by the two resident CTAs), not by the fabric.  The launcher
+    // therefore uses clusters of 1; DFW_TC_CLUSTER=2|4 keeps the path testable.
+    const uint32_t csize = cluster_nctarank(), crank = csize > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]);
@@ -113,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], csize);
             mbar_init(&conv[s], 128);
         }
         mbar_init(accum_full, 1);
@@ -136,7 +162,9 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     fence_tc_before();
     __syncthreads();
     fence_tc_after();
+    if (csize > 1) cluster_sync_all();  // peers' barriers exist before anything is multicast to them
     const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 0) PROBE(0);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -151,8 +179,13 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 uint8_t* st = smem + (size_t)stage * L.stage_bytes;
                 mbar_arrive_expect_tx(&full[stage], stage_tx);
                 tma_load_2d(st + L.a_hi, &maps.a[seg], &full[stage], kc, (int)m_base);
-                tma_load_2d(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0);
-                if (TF32) tma_load_2d(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0);
+                if (csize == 1) {
+                    tma_load_2d(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0);
+                    if (TF32) tma_load_2d(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0);
+                } else if (crank == 0) {
+                    tma_load_2d_mc(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0, cmask);
+                    if (TF32) tma_load_2d_mc(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0, cmask);
+                }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
             if (p.residual) {
@@ -184,6 +217,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             for (int c = 0; c < total_chunks; ++c) {
                 mbar_wait(TF32 ? &conv[stage] : &full[stage], phase);
                 fence_tc_after();
+                if (c < 20) PROBE(1 + c);  // operands of chunk c ready
                 const uint32_t st = smem_u32(smem + (size_t)stage * L.stage_bytes);
 #pragma unroll
                 for (int k = 0; k < CB / 32; ++k) {  // UMMA_K = 32 bytes (16 bf16 / 8 tf32); +32 B = +2 in the address field
@@ -214,7 +248,9 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                     }
                     accumulate = 1u;
                 }
-                umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+                // frees the smem stage once these MMAs have read it (in a cluster: tells every peer)
+                if (csize == 1) umma_commit(&empty[stage]);
+                else umma_commit_mc(&empty[stage], cmask);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
             umma_commit(accum_full);
@@ -227,6 +263,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             uint32_t phase = 0;
             for (int c = 0; c < total_chunks; ++c) {
                 mbar_wait(&full[stage], phase);
+                if (et == 0 && c < 20) PROBE(21 + c);  // TMA data of chunk c landed
                 uint8_t* st = smem + (size_t)stage * L.stage_bytes;
                 float4* hi = reinterpret_cast<float4*>(st + L.a_hi);
                 float4* lo = reinterpret_cast<float4*>(st + L.a_lo);
@@ -243,6 +280,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
 
         mbar_wait(accum_full, 0);
         fence_tc_after();
+        if (et == 0) PROBE(41);  // accumulator complete
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int r_in_tile = q * 32 + lane;
         const int64_t row = m_base + r_in_tile;
@@ -250,6 +288,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const int H = p.Hout;
         if (TF32) tmem_combine(t_row, H, p.nacc + 1, p.Npad);
+        if (et == 0) PROBE(42);  // hi/cross accumulators combined
         const int n32 = H / 32;
         const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
         const bool ln = p.flags & DFW_EP_LAYERNORM;
@@ -329,6 +368,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             }
             mean = s / (float)H;
         }
+        if (et == 0) PROBE(43);  // pass 1 (pre-activation staged + stored)
         // ---- pass 2: variance around the mean (two-pass, like torch) ----
         if (ln) {
             float qs = 0.f;
@@ -347,8 +387,10 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 p.ln_stats[2 * row + 1] = rstd;
             }
         }
+        if (et == 0) PROBE(44);  // pass 2 (variance)
         // ---- pass 3: normalise, ReLU, dropout, row-dot, residual, store ----
         if (p.residual) mbar_wait(res_full, 0);
+        if (et == 0) PROBE(45);  // residual tile in smem
         float dot = 0.f;
         for (int ob = 0; ob < out_boxes; ++ob) {
             uint8_t* box = p.out ? acquire_box() : nullptr;
@@ -413,7 +455,9 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             if (p.out) release_box(&maps.out, box, ob * EPC);
         }
         if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
+        if (et == 0) PROBE(46);  // pass 3 done
         if (et == 0) tma_store_wait_read<0>();  // smem must outlive the bulk stores' reads
+        if (et == 0) PROBE(47);
     }
 
     fence_tc_before();
@@ -422,6 +466,8 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         fence_tc_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
+    if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
+    if (threadIdx.x == 0) PROBE(48);
 }
 
 // ---- weight preparation: (optional transpose) + TF32 hi/lo split, or plain copy/transpose for bf16 ----
@@ -447,6 +493,16 @@ __global__ void k_prep_weight(const T* __restrict__ w, int rows, int cols, int t
         }
     }
 }
+
+#ifdef DFW_TC_PROBE
+}  // namespace tc
+}  // namespace dfw
+extern "C" int dfw_tc_set_probe(long long* dev_buf) {
+    return cudaMemcpyToSymbol(dfw::tc::g_probe, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : 1;
+}
+namespace dfw {
+namespace tc {
+#endif
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -591,15 +647,30 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
     while (stages > 2 && stages > total_chunks && fits(stages - 1, 225 * 1024)) --stages;
     args.stages = stages;
     const size_t smem = carve(tf32, args.Npad, stages, out_boxes).total + 1024;
-    const unsigned grid = (unsigned)((args.N + kTileM - 1) / kTileM);
+    const unsigned tiles = (unsigned)((args.N + kTileM - 1) / kTileM);
+    static const int env_cluster = [] { const char* e = getenv("DFW_TC_CLUSTER"); return e ? atoi(e) : 0; }();  // dev probe
+    unsigned cluster = env_cluster > 0 ? (unsigned)env_cluster : 1u;
+    if (tiles < 2 * cluster) cluster = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((tiles + cluster - 1) / cluster * cluster, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (tf32) {
         auto kern = k_linear_tc<float, true>;
         DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, s>>>(maps, args);
+        DFW_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, args));
     } else {
         auto kern = k_linear_tc<__nv_bfloat16, false>;
         DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, s>>>(maps, args);
+        DFW_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, args));
     }
     DFW_LAUNCH_CHECK();
     return 0;

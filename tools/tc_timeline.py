@@ -1,10 +1,13 @@
 #!/usr/bin/env python3
-import os, sys, torch
+"""Per-phase timeline of ONE mid-grid CTA of the tcgen05 linear kernel (development aid).
+Needs a probe build:  make -C deep-fem-uav-wing_b200/csrc clean && make -C deep-fem-uav-wing_b200/csrc EXTRA=-DDFW_TC_PROBE"""
+import ctypes, os, sys, torch
 REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path[:0] = [REPO, os.path.join(REPO, "deep-fem-uav-wing_b200")]
-dbg = torch.zeros(128, dtype=torch.int64, device="cuda")
-os.environ["DFW_TC_DEBUG"] = str(dbg.data_ptr())
-from deep_fem_uav_wing.gnn import ops
+from deep_fem_uav_wing.gnn import ops, _cabi
+dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+_cabi.lib.dfw_tc_set_probe.argtypes = [ctypes.c_void_p]
+assert _cabi.lib.dfw_tc_set_probe(dbg.data_ptr()) == 0
 n, H = 200000, 128
 for dt in (torch.float32, torch.bfloat16):
     x = torch.randn(n, H, device="cuda").to(dt); agg = torch.randn(n, H, device="cuda").to(dt)
@@ -12,14 +15,13 @@ for dt in (torch.float32, torch.bfloat16):
     g, be = torch.ones(H, device="cuda"), torch.zeros(H, device="cuda")
     for _ in range(3):
         dbg.zero_()
-        ops.linear_fwd(agg, w, x, w, bias=b, ln=(g, be), relu=True, residual=x, save_pre=True)
+        ops.linear_fwd(agg, w, x, w, bias=b, ln=(g, be), relu=True, residual=x, save_pre=True, dropout_p=0.1, seed=3)
         torch.cuda.synchronize()
     d = dbg.cpu().tolist()
-    t0 = d[66]
-    rel = lambda v: v - t0 if v else None
-    print(dt, "start->", "tma issue:", [rel(v) for v in d[0:8]])
-    print("   conv start:", [rel(v) for v in d[16:24]])
-    print("   conv done :", [rel(v) for v in d[32:40]])
-    print("   mma start :", [rel(v) for v in d[48:56]])
-    print("   accum_full:", rel(d[64]), " epilogue done:", rel(d[65]))
-    print("   epi stamps: tmem_loaded", rel(d[70]), "bias_done", rel(d[71]), "pre_stored", rel(d[72]), "ln_relu_done", rel(d[73]), "out_acquired", rel(d[74]), "res_ready", rel(d[75]), "out_staged", rel(d[76]), "out_issued", rel(d[77]))
+    t0 = d[0]
+    rel = lambda v: (v - t0) if v else None
+    print(dt, "ns since the CTA's setup barrier")
+    print("   TMA data landed (chunk c):", [rel(v) for v in d[21:41]])
+    print("   MMA operands ready       :", [rel(v) for v in d[1:21]])
+    print("   accum_full", rel(d[41]), "combined", rel(d[42]), "pass1", rel(d[43]), "pass2", rel(d[44]), "res_ready", rel(d[45]),
+          "pass3", rel(d[46]), "stores_read", rel(d[47]), "exit", rel(d[48]))
