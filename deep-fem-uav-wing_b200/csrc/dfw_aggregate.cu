@@ -51,6 +51,12 @@ struct Acc<float> {
         asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a[0]) : "l"(lo));
         asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a[1]) : "l"(hi));
     }
+    __device__ __forceinline__ void fma(const uint4& v, float s) {  // acc += s * v (packed FFMA2)
+        const uint64_t lo = ((uint64_t)v.y << 32) | v.x, hi = ((uint64_t)v.w << 32) | v.z;
+        const uint64_t ss = ((uint64_t)__float_as_uint(s) << 32) | __float_as_uint(s);
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[0]) : "l"(lo), "l"(ss));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[1]) : "l"(hi), "l"(ss));
+    }
     __device__ __forceinline__ void get(float* f) const {
         f[0] = __uint_as_float((uint32_t)a[0]); f[1] = __uint_as_float((uint32_t)(a[0] >> 32));
         f[2] = __uint_as_float((uint32_t)a[1]); f[3] = __uint_as_float((uint32_t)(a[1] >> 32));
@@ -72,6 +78,14 @@ struct Acc<__nv_bfloat16> {
             asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(w[i]));
             asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(a[2 * i]) : "h"(lo));      // FHADD.BF16: f32 += bf16
             asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(a[2 * i + 1]) : "h"(hi));
+        }
+    }
+    __device__ __forceinline__ void fma(const uint4& v, float s) {  // acc += s * v
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[2 * i] = fmaf(__uint_as_float(w[i] << 16), s, a[2 * i]);
+            a[2 * i + 1] = fmaf(__uint_as_float(w[i] & 0xffff0000u), s, a[2 * i + 1]);
         }
     }
     __device__ __forceinline__ void get(float* f) const {
@@ -101,9 +115,11 @@ struct Acc<__nv_bfloat16> {
 //    memory) can lift it further.
 //  * PIPE (batch b+1 in flight while batch b is added) is kept as a template switch: it helps at 16 warps but
 //    32 warps x one batch hide the per-block prologue (rowptr -> col -> rows) better (745 vs 956 us).
-template <typename T, int LANES, int VPL, bool HAS_ADD, bool EXACT, int kAggThreads, int KUDIV, bool PIPE>
+template <typename T, int LANES, int VPL, bool HAS_ADD, bool EXACT, bool HAS_SRC, int kAggThreads, int KUDIV, bool PIPE>
 __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                              const float* __restrict__ row_scale, const T* __restrict__ x,
+                                                              const float* __restrict__ row_scale,
+                                                              const float* __restrict__ src_scale /*per SOURCE row (HAS_SRC)*/,
+                                                              const T* __restrict__ x,
                                                               const T* __restrict__ addend, T* __restrict__ out, int64_t N,
                                                               int nvec /*16B vectors per row*/, int R /*rows per group, < LANES*/) {
     using V = Vec16<T>;
@@ -113,8 +129,10 @@ __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __r
     constexpr int kU1 = kU0 / KUDIV < 2 ? 2 : kU0 / KUDIV;
     constexpr int kU = kU1 < LANES ? kU1 : LANES;
     static_assert(LANES % kU == 0, "a column window holds whole batches");
+    static_assert(!(PIPE && HAS_SRC), "the per-batch scales live in one register set");
     __shared__ int s_next;
     __shared__ __align__(16) int s_cols[kAggThreads / 32][2][32];
+    __shared__ __align__(16) float s_scl[HAS_SRC ? kAggThreads / 32 : 1][2][32];  // the columns' source scales
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
     const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane / LANES * LANES));
@@ -143,6 +161,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __r
     const char* al = reinterpret_cast<const char*>(al_);
     char* ol = reinterpret_cast<char*>(ol_);
     int* const wcols = &s_cols[threadIdx.x >> 5][0][lane - sub];  // this group's slice of the two column windows
+    float* const wscl = &s_scl[HAS_SRC ? threadIdx.x >> 5 : 0][0][lane - sub];
 
   for (;;) {
     int blk = 0;
@@ -211,18 +230,51 @@ __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __r
     const int nbatch = (ne + kU - 1) / kU;
     // lanes past the end of the edge range repeat the last valid column (a harmless L1 hit), so every slot of a
     // window holds a loadable column and a batch needs no bounds checks
-    int mine = ne > 0 ? ldg_stream_s32(col + e_beg + min(sub, min(LANES, ne) - 1)) : 0;
+    auto load_cols = [&](int j) { return ldg_stream_s32(col + e_beg + j + min(sub, min(LANES, ne - j) - 1)); };
+    int mine = ne > 0 ? load_cols(0) : 0;
+    // HAS_SRC: the scale of a column is a dependent load, so the columns run TWO windows ahead of the rows and the
+    // scales one window ahead: neither round trip is waited for
+    float smine = 0.f;
+    int mine_nxt = 0;
+    if (HAS_SRC && ne > 0) {
+        smine = __ldg(src_scale + mine);
+        if (LANES < ne) mine_nxt = load_cols(LANES);
+    }
     // request the rows of batch b into `buf`; the first batch of a column window parks the window in shared memory
     // and requests the next window's columns
+    float sb[HAS_SRC ? kU : 1];
     auto issue = [&](uint4 (&buf)[kU][VPL], int b) {
         const int j = b * kU;
         const int within = j & (LANES - 1);
-        int* w = wcols + ((j / LANES) & 1) * 32;
+        const int wsel = ((j / LANES) & 1) * 32;
+        int* w = wcols + wsel;
         if (within == 0) {
             w[sub] = mine;
+            if (HAS_SRC) wscl[wsel + sub] = smine;
             __syncwarp(gmask);
             const int nxt = j + LANES;
-            if (nxt < ne) mine = ldg_stream_s32(col + e_beg + nxt + min(sub, min(LANES, ne - nxt) - 1));
+            if (HAS_SRC) {
+                if (nxt < ne) {
+                    mine = mine_nxt;
+                    smine = __ldg(src_scale + mine);
+                    if (nxt + LANES < ne) mine_nxt = load_cols(nxt + LANES);
+                }
+            } else if (nxt < ne) {
+                mine = load_cols(nxt);
+            }
+        }
+        if constexpr (HAS_SRC) {
+            const float* ws_ = wscl + wsel + within;
+            if constexpr (kU == 8) {
+                const float4 s0 = *reinterpret_cast<const float4*>(ws_), s1 = *reinterpret_cast<const float4*>(ws_ + 4);
+                sb[0] = s0.x; sb[1] = s0.y; sb[2] = s0.z; sb[3] = s0.w; sb[4] = s1.x; sb[5] = s1.y; sb[6] = s1.z; sb[7] = s1.w;
+            } else if constexpr (kU == 4) {
+                const float4 s0 = *reinterpret_cast<const float4*>(ws_);
+                sb[0] = s0.x; sb[1] = s0.y; sb[2] = s0.z; sb[3] = s0.w;
+            } else {
+                const float2 s0 = *reinterpret_cast<const float2*>(ws_);
+                sb[0] = s0.x; sb[1] = s0.y;
+            }
         }
         uint32_t cb[kU];
         if constexpr (kU == 8) {
@@ -248,14 +300,20 @@ __global__ void __launch_bounds__(kAggThreads, 1) k_aggregate(const int32_t* __r
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) acc[v].add(buf[u][v]);
+                for (int v = 0; v < VPL; ++v) {
+                    if constexpr (HAS_SRC) acc[v].fma(buf[u][v], sb[u]);
+                    else acc[v].add(buf[u][v]);
+                }
             }
         } else {
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 while (ebase + u == cur_end) flush();  // group-uniform; also steps over empty rows
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) acc[v].add(buf[u][v]);
+                for (int v = 0; v < VPL; ++v) {
+                    if constexpr (HAS_SRC) acc[v].fma(buf[u][v], sb[u]);
+                    else acc[v].add(buf[u][v]);
+                }
             }
         }
     };
@@ -308,8 +366,8 @@ inline int pick_rows_per_group(int64_t N, int64_t E, int lanes, int groups, int 
 constexpr int kAggThreads = 1024;
 
 template <typename T, int LANES, int VPL>
-int launch(const int32_t* rowptr, const int32_t* col, const float* row_scale, const void* x, const void* addend,
-           void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
+int launch(const int32_t* rowptr, const int32_t* col, const float* row_scale, const float* src_scale, const void* x,
+           const void* addend, void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
     constexpr int GROUPS = 32 / LANES;
     const int R = pick_rows_per_group(N, E, LANES, GROUPS, kAggThreads);
     const int64_t chunk_rows = (int64_t)R * GROUPS * (kAggThreads / 32);
@@ -317,13 +375,15 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* row_scale, co
     const int64_t blocks = std::min<int64_t>(chunks, kNumSMs);
     if (blocks == 0) return 0;
     const bool exact = nvec == LANES * VPL;
-#define DFW_AGG_GO(A, X)                                                                                                       \
-    k_aggregate<T, LANES, VPL, A, X, kAggThreads, 1, false><<<(unsigned)blocks, kAggThreads, 0, s>>>(rowptr, col, row_scale, (const T*)x, \
-                                                                                                     (const T*)addend, (T*)out, N, nvec, R)
-    if (exact) {
-        if (addend) DFW_AGG_GO(true, true); else DFW_AGG_GO(false, true);
+#define DFW_AGG_GO(A, X, S)                                                                                                  \
+    k_aggregate<T, LANES, VPL, A, X, S, kAggThreads, 1, false><<<(unsigned)blocks, kAggThreads, 0, s>>>(                         \
+        rowptr, col, row_scale, src_scale, (const T*)x, (const T*)addend, (T*)out, N, nvec, R)
+    if (src_scale) {  // (the scaled gather is only used without an addend: backward of the mean)
+        if (exact) DFW_AGG_GO(false, true, true); else DFW_AGG_GO(false, false, true);
+    } else if (exact) {
+        if (addend) DFW_AGG_GO(true, true, false); else DFW_AGG_GO(false, true, false);
     } else {
-        if (addend) DFW_AGG_GO(true, false); else DFW_AGG_GO(false, false);
+        if (addend) DFW_AGG_GO(true, false, false); else DFW_AGG_GO(false, false, false);
     }
 #undef DFW_AGG_GO
     DFW_LAUNCH_CHECK();
@@ -331,9 +391,9 @@ int launch(const int32_t* rowptr, const int32_t* col, const float* row_scale, co
 }
 
 template <typename T>
-int dispatch(const int32_t* rowptr, const int32_t* col, const float* row_scale, const void* x, const void* addend,
-             void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
-#define DFW_AGG(L, V) return launch<T, L, V>(rowptr, col, row_scale, x, addend, out, N, E, nvec, s)
+int dispatch(const int32_t* rowptr, const int32_t* col, const float* row_scale, const float* src_scale, const void* x,
+             const void* addend, void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
+#define DFW_AGG(L, V) return launch<T, L, V>(rowptr, col, row_scale, src_scale, x, addend, out, N, E, nvec, s)
     if (nvec <= 4) DFW_AGG(4, 1);
     if (nvec <= 8) DFW_AGG(8, 1);
     if (nvec <= 16) DFW_AGG(16, 1);
@@ -348,23 +408,35 @@ int dispatch(const int32_t* rowptr, const int32_t* col, const float* row_scale, 
 }  // namespace
 }  // namespace dfw
 
+static int aggregate_entry(const char* who, const int32_t* rowptr, const int32_t* col, const float* row_scale,
+                           const float* src_scale, const void* x, const void* addend, void* out, int64_t N, int64_t E, int64_t H,
+                           int dtype, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(N >= 0 && E >= 0 && H > 0, "%s: bad shape N=%lld E=%lld H=%lld", who, (long long)N, (long long)E, (long long)H);
+    DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "%s: unknown dtype %d", who, dtype);
+    const int64_t row_bytes = H * (dtype == DFW_F32 ? 4 : 2);
+    DFW_REQUIRE(row_bytes % 16 == 0, "%s: H*sizeof(dtype) = %lld must be a multiple of 16", who, (long long)row_bytes);
+    if (N == 0) return 0;
+    DFW_REQUIRE(rowptr && (col || E == 0) && x && out, "%s: null pointer", who);
+    DFW_REQUIRE(aligned16(x) && aligned16(out) && (!addend || aligned16(addend)), "%s: x/out/addend must be 16-byte aligned", who);
+    DFW_REQUIRE(N * (row_bytes / 16) < (1LL << 40), "%s: tensor too large", who);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int nvec = (int)(row_bytes / 16);
+    if (dtype == DFW_F32) return dispatch<float>(rowptr, col, row_scale, src_scale, x, addend, out, N, E, nvec, s);
+    return dispatch<__nv_bfloat16>(rowptr, col, row_scale, src_scale, x, addend, out, N, E, nvec, s);
+}
+
 extern "C" int dfw_sage_aggregate(const int32_t* rowptr, const int32_t* col, const float* row_scale, const void* x,
                                   const void* addend, void* out, int64_t N, int64_t E, int64_t H, int dtype,
                                   dfw_stream_t stream) {
-    using namespace dfw;
-    DFW_REQUIRE(N >= 0 && E >= 0 && H > 0, "dfw_sage_aggregate: bad shape N=%lld E=%lld H=%lld", (long long)N, (long long)E,
-                (long long)H);
-    DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_sage_aggregate: unknown dtype %d", dtype);
-    const int64_t row_bytes = H * (dtype == DFW_F32 ? 4 : 2);
-    DFW_REQUIRE(row_bytes % 16 == 0, "dfw_sage_aggregate: H*sizeof(dtype) = %lld must be a multiple of 16",
-                (long long)row_bytes);
-    if (N == 0) return 0;
-    DFW_REQUIRE(rowptr && (col || E == 0) && x && out, "dfw_sage_aggregate: null pointer");
-    DFW_REQUIRE(aligned16(x) && aligned16(out) && (!addend || aligned16(addend)),
-                "dfw_sage_aggregate: x/out/addend must be 16-byte aligned");
-    DFW_REQUIRE(N * (row_bytes / 16) < (1LL << 40), "dfw_sage_aggregate: tensor too large");
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const int nvec = (int)(row_bytes / 16);
-    if (dtype == DFW_F32) return dispatch<float>(rowptr, col, row_scale, x, addend, out, N, E, nvec, s);
-    return dispatch<__nv_bfloat16>(rowptr, col, row_scale, x, addend, out, N, E, nvec, s);
+    return aggregate_entry("dfw_sage_aggregate", rowptr, col, row_scale, nullptr, x, addend, out, N, E, H, dtype, stream);
+}
+
+extern "C" int dfw_sage_aggregate_scaled(const int32_t* rowptr, const int32_t* col, const float* src_scale, const void* x,
+                                         void* out, int64_t N, int64_t E, int64_t H, int dtype, dfw_stream_t stream) {
+    if (N > 0 && !src_scale) {
+        dfw::set_error("dfw_sage_aggregate_scaled: src_scale is NULL");
+        return 1;
+    }
+    return aggregate_entry("dfw_sage_aggregate_scaled", rowptr, col, nullptr, src_scale, x, nullptr, out, N, E, H, dtype, stream);
 }

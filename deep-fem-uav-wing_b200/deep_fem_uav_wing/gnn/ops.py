@@ -226,6 +226,21 @@ def aggregate(rowptr, col, row_scale, x, addend=None):
     return out
 
 
+def aggregate_scaled(rowptr, col, src_scale, x):
+    """``out[i] = sum_k src_scale[col[k]] * x[col[k]]`` (``dfw_sage_aggregate_scaled``)."""
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    N, H = x.shape
+    E = col.shape[0]
+    amin = 2 * N * H * _esz(x) + 4 * E + 4 * (N + 1) + 4 * N
+    with torch.cuda.device(x.device), _prof("aggregate", amin):
+        check(lib.dfw_sage_aggregate_scaled(rowptr.data_ptr(), col.data_ptr(), src_scale.data_ptr(), x.data_ptr(), out.data_ptr(),
+                                            N, E, H, _dt(x), _stream(x)))
+    LAUNCH_COUNTER["kernels"] += 1
+    return out
+
+
 def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=False, residual=None, dropout_p=0.0, seed=0,
                save_pre=False, rowdot=None, want_out=True):
     """See ``dfw_linear_fwd``.  ``ln`` = (gamma, beta); ``rowdot`` = (w fp32 [Hout], b fp32 [1] or None)."""
@@ -412,10 +427,14 @@ class SageConvFn(torch.autograd.Function):
             dwl, dwr, dbl = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias)
         g_x = None
         if ctx.needs_input_grad[0]:
-            g_agg = linear_bwd_input(g_y, wl, row_scale=graph.inv_deg)
-            g_root = linear_bwd_input(g_y, wr, addend=g_out if ctx.fused_tail else None)
+            # dL/dx = A^T D^-1 (g_y W_l) + g_y W_r (+ g_out) = (A^T D^-1 g_y) W_l + g_y W_r (+ g_out): aggregate the
+            # gradient FIRST (scale on the source side), then ONE two-operand linear with the residual epilogue -
+            # the forward's own kernel shape - instead of two contractions and an aggregation with an addend
+            # (8 -> 6 passes over [N, H] tensors).
             rp_t, col_t = graph.transpose()
-            g_x = aggregate(rp_t, col_t, None, g_agg, addend=g_root)
+            g_t = aggregate_scaled(rp_t, col_t, graph.inv_deg, g_y)
+            g_x, _, _, _ = linear_fwd(g_t, wl.t().contiguous(), g_y, wr.t().contiguous(),
+                                      residual=g_out if ctx.fused_tail else None)
         return g_x, dwl, dbl, dwr, dgamma, dbeta, None, None, None, None, None
 
 

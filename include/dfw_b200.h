@@ -73,6 +73,15 @@ int dfw_sage_aggregate(const int32_t* rowptr, const int32_t* col, const float* r
                        const void* x, const void* addend, void* out,
                        int64_t N, int64_t E, int64_t H, int dtype, dfw_stream_t stream);
 
+/* Same gather with the scale on the SOURCE side:  out[i,:] = sum_{k in row i} src_scale[col[k]] * x[col[k],:]
+ * With the transposed CSR and src_scale = inv_deg this is A^T D^-1 g, the adjoint of the mean aggregation applied to
+ * the gradient BEFORE the weight contraction:  dL/dh = (A^T D^-1 g_y) lin_l.weight + g_y lin_r.weight  - one
+ * aggregation of g_y followed by one fused two-operand linear, instead of two contractions and an aggregation
+ * (autograd of SAGEConv, reference call site model.py:90 / loss.backward() train_gnn.py:57). */
+int dfw_sage_aggregate_scaled(const int32_t* rowptr, const int32_t* col, const float* src_scale,
+                              const void* x, void* out,
+                              int64_t N, int64_t E, int64_t H, int dtype, dfw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (c) fused node-wise linear:
  *        y   = a1 . w1^T (+ a2 . w2^T) (+ bias)                       [N,Hout]

@@ -106,6 +106,12 @@ def test_aggregate_matches_oracle(ops, h, dtype):
     ref_t = torch.from_numpy(csr_aggregate_c(ot[0], ot[1], None, x.float().numpy())) + add.float()
     got_t = ops.aggregate(rp_t, col_t, None, x.cuda(), addend=add.cuda())
     assert rel_max(got_t.float().cpu(), ref_t) < tol
+    # source-scaled gather (adjoint of the mean): sum_k inv_deg[col[k]] * x[col[k]] over the transposed CSR
+    inv_t = torch.from_numpy(inv)
+    ref_s = torch.from_numpy(csr_aggregate_c(ot[0], ot[1], None, (x.float() * inv_t[:, None]).numpy()))
+    got_s = ops.aggregate_scaled(rp_t, col_t, g.inv_deg, x.cuda())
+    assert rel_max(got_s.float().cpu(), ref_s) < tol
+    assert torch.equal(got_s, ops.aggregate_scaled(rp_t, col_t, g.inv_deg, x.cuda()))
 
 
 def test_aggregate_properties_at_scale(ops):
@@ -128,6 +134,9 @@ def test_aggregate_properties_at_scale(ops):
     aty = ops.aggregate(rp_t, col_t, None, y * g.inv_deg[:, None])
     lhs, rhs = (ax.double() * y.double()).sum().item(), (x.double() * aty.double()).sum().item()
     assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0)
+    # the source-scaled gather is the same adjoint without the pre-scaled copy
+    aty2 = ops.aggregate_scaled(rp_t, col_t, g.inv_deg, y)
+    assert rel_max(aty2, aty) < TOL_FP32
     # permutation equivariance
     perm = torch.randperm(n, device="cuda", generator=gen)
     inv = torch.empty_like(perm)
