@@ -325,8 +325,23 @@ def main():
         kernels[name] = ent
     dom = max(summ, key=lambda k: summ[k]["ms"])
     d = kernels[dom]
+    # DRAM traffic per launch of the same kernel on the same shapes, from the committed `ncu --set full` captures
+    # (tools/ncu_capture_all.sh -> tools/ncu_summary.py --json); null when no capture of that kernel is on file
+    traffic, traffic_src = None, None
+    tpath = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")
+    cap = {"aggregate": "r01b_agg_cfg2", "aggregate_bwd": "r01b_aggs_cfg2", "linear_fwd": "r01b_lin_fwd_fp32",
+           "linear_bwd_input": "r01b_lin_fwd_fp32", "linear_bwd_weight": "r01b_dw_fp32", "epilogue_bwd": "r01b_epi_bwd_fp32"}
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        for name, ent in kernels.items():
+            c = tj.get(cap.get(name, ""))
+            if c:
+                ent["ncu_dram_bytes_per_launch"] = c["dram_bytes"]
+        if cap.get(dom) in tj:
+            traffic, traffic_src = tj[cap[dom]]["dram_bytes"], f"profiles/r01_ncu_traffic.json:{cap[dom]}"
     roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": d["hbm_frac"], "traffic": None, "peak_source": pk["_source"],
+                "frac": d["hbm_frac"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": summ[dom]["bytes"] / summ[dom]["calls"], "peak_source": pk["_source"],
                 "note": "algorithmic bytes per launch (DESIGN.md) / mean CUDA-event duration; every kernel of the step is listed under `kernels`"}
 
     # ---- arm 2: end to end through the public API from pinned host memory ----------------------

@@ -471,9 +471,21 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
 }
 
 // ---- weight preparation: (optional transpose) + TF32 hi/lo split, or plain copy/transpose for bf16 ----
+// One launch prepares BOTH operands' weights (blockIdx.y = operand): the per-call preparation used to be two
+// ~3 us launches in front of every linear.
+struct PrepArgs {
+    const void* w[2];
+    void* hi[2];
+    void* lo[2];
+    int rows[2], cols[2];
+};
 template <typename T>
-__global__ void k_prep_weight(const T* __restrict__ w, int rows, int cols, int transpose, int split, T* __restrict__ hi,
-                              T* __restrict__ lo) {
+__global__ void k_prep_weight(const PrepArgs a, int transpose, int split) {
+    const int op = blockIdx.y;
+    const T* __restrict__ w = static_cast<const T*>(a.w[op]);
+    T* __restrict__ hi = static_cast<T*>(a.hi[op]);
+    T* __restrict__ lo = static_cast<T*>(a.lo[op]);
+    const int rows = a.rows[op], cols = a.cols[op];
     const int64_t n = (int64_t)rows * cols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         // output index i over [orow, ocol] where out = transpose ? w^T : w
@@ -586,19 +598,23 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
     const void* wsrc[2] = {w1, w2};
     const int64_t ks[2] = {k1, a2 ? k2 : 0};
     const void* wuse[2] = {w1, w2};
-    for (int i = 0; i < (a2 ? 2 : 1); ++i) {
-        const bool need_prep = tf32 || transpose_w;
-        if (!need_prep) continue;
-        const int rows = transpose_w ? (int)ks[i] : (int)Hout, cols = transpose_w ? (int)Hout : (int)ks[i];
-        const int64_t n = (int64_t)rows * cols;
-        const int blocks = (int)std::min<int64_t>((n + 255) / 256, kNumSMs * 4);
-        if (tf32)
-            k_prep_weight<float><<<blocks, 256, 0, s>>>((const float*)wsrc[i], rows, cols, transpose_w, 1, (float*)hi[i], (float*)lo[i]);
-        else
-            k_prep_weight<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)wsrc[i], rows, cols, transpose_w, 0,
-                                                              (__nv_bfloat16*)hi[i], (__nv_bfloat16*)lo[i]);
+    if (tf32 || transpose_w) {
+        const int nops = a2 ? 2 : 1;
+        PrepArgs pa{};
+        int64_t nmax = 0;
+        for (int i = 0; i < nops; ++i) {
+            pa.w[i] = wsrc[i];
+            pa.hi[i] = hi[i];
+            pa.lo[i] = lo[i];
+            pa.rows[i] = transpose_w ? (int)ks[i] : (int)Hout;
+            pa.cols[i] = transpose_w ? (int)Hout : (int)ks[i];
+            nmax = std::max<int64_t>(nmax, (int64_t)pa.rows[i] * pa.cols[i]);
+            wuse[i] = hi[i];
+        }
+        const dim3 pgrid((unsigned)std::min<int64_t>((nmax + 255) / 256, kNumSMs * 4), (unsigned)nops, 1);
+        if (tf32) k_prep_weight<float><<<pgrid, 256, 0, s>>>(pa, transpose_w, 1);
+        else k_prep_weight<__nv_bfloat16><<<pgrid, 256, 0, s>>>(pa, transpose_w, 0);
         DFW_LAUNCH_CHECK();
-        wuse[i] = hi[i];
     }
 
     Maps maps;

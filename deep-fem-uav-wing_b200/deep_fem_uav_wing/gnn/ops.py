@@ -226,7 +226,7 @@ def aggregate(rowptr, col, row_scale, x, addend=None):
     return out
 
 
-def aggregate_scaled(rowptr, col, src_scale, x):
+def aggregate_scaled(rowptr, col, src_scale, x, label="aggregate_bwd"):
     """``out[i] = sum_k src_scale[col[k]] * x[col[k]]`` (``dfw_sage_aggregate_scaled``)."""
     _require_cuda(x, "x")
     x = x.contiguous()
@@ -234,7 +234,7 @@ def aggregate_scaled(rowptr, col, src_scale, x):
     N, H = x.shape
     E = col.shape[0]
     amin = 2 * N * H * _esz(x) + 4 * E + 4 * (N + 1) + 4 * N
-    with torch.cuda.device(x.device), _prof("aggregate", amin):
+    with torch.cuda.device(x.device), _prof(label, amin):
         check(lib.dfw_sage_aggregate_scaled(rowptr.data_ptr(), col.data_ptr(), src_scale.data_ptr(), x.data_ptr(), out.data_ptr(),
                                             N, E, H, _dt(x), _stream(x)))
     LAUNCH_COUNTER["kernels"] += 1
@@ -242,7 +242,7 @@ def aggregate_scaled(rowptr, col, src_scale, x):
 
 
 def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=False, residual=None, dropout_p=0.0, seed=0,
-               save_pre=False, rowdot=None, want_out=True):
+               save_pre=False, rowdot=None, want_out=True, label="linear_fwd"):
     """See ``dfw_linear_fwd``.  ``ln`` = (gamma, beta); ``rowdot`` = (w fp32 [Hout], b fp32 [1] or None)."""
     _require_cuda(a1, "input")
     N, k1 = a1.shape
@@ -269,7 +269,7 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=Fals
         + Hout * (k1 + k2) * es
     ws_bytes = lib.dfw_linear_ws_bytes(Hout, k1, k2, _dt(a1))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev), _prof("linear_fwd", nbytes, 2 * N * Hout * (k1 + k2)):
+    with torch.cuda.device(dev), _prof(label, nbytes, 2 * N * Hout * (k1 + k2)):
         check(lib.dfw_linear_fwd(
             a1.data_ptr(), w1.data_ptr(), k1, _ptr(a2), _ptr(w2), 0 if a2 is None else a2.shape[1], _ptr(bias),
             _ptr(ln[0]) if ln is not None else None, _ptr(ln[1]) if ln is not None else None, float(eps), _ptr(residual),
@@ -434,7 +434,7 @@ class SageConvFn(torch.autograd.Function):
             rp_t, col_t = graph.transpose()
             g_t = aggregate_scaled(rp_t, col_t, graph.inv_deg, g_y)
             g_x, _, _, _ = linear_fwd(g_t, wl.t().contiguous(), g_y, wr.t().contiguous(),
-                                      residual=g_out if ctx.fused_tail else None)
+                                      residual=g_out if ctx.fused_tail else None, label="linear_bwd_input")
         return g_x, dwl, dbl, dwr, dgamma, dbeta, None, None, None, None, None
 
 

@@ -26,8 +26,9 @@ if what.startswith("linear"):
         for _ in range(3):
             ops.linear_bwd_input(x, w, row_scale=b.new_ones(n))
     if "dw" in what:
+        gy = torch.randn(n, H, device="cuda").to(dt)
         for _ in range(3):
-            ops.linear_bwd_weight(x, agg, x, want_bias=False)
+            ops.linear_bwd_weight(gy, agg, x, want_bias=False)
     if "epi" in what:
         pre = torch.randn(n, H, device="cuda").to(dt)
         stats = torch.rand(n, 2, device="cuda") + 0.5
@@ -43,7 +44,12 @@ elif what.startswith("agg"):
     ei = torch.from_numpy(mesh["edge_index"]).cuda()
     g = ops.get_graph(ei, mesh["num_nodes"])
     x = torch.randn(mesh["num_nodes"], H, device="cuda").to(dt)
-    for _ in range(3):
-        ops.aggregate(g.rowptr, g.col, g.inv_deg, x)
+    if what.startswith("aggs"):  # source-scaled gather over the transposed CSR (backward)
+        rp_t, col_t = g.transpose()
+        for _ in range(3):
+            ops.aggregate_scaled(rp_t, col_t, g.inv_deg, x)
+    else:
+        for _ in range(3):
+            ops.aggregate(g.rowptr, g.col, g.inv_deg, x)
 torch.cuda.synchronize()
 print("ok", what)
