@@ -44,6 +44,9 @@ SIGNATURES = {
                                    c_size_t, c_void_p]),
     "dfw_masked_mse_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_void_p, c_void_p]),
+    "dfw_stress_metrics_ws_bytes": (c_size_t, [c_int64, c_int64]),
+    "dfw_stress_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
     "dfw_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
 }
 

@@ -172,10 +172,26 @@ class MaskedMSELoss(nn.Module):
         return loss
 
 
+def metrics_from_device(result: torch.Tensor) -> dict:
+    """8 doubles of ``ops.stress_metrics`` -> the reference's nested dict (``model.py:206-216``).  One D2H copy."""
+    r = result.detach().cpu().tolist()
+
+    def sub(o):
+        return {"mae": float(r[o]), "rmse": float(r[o + 1]), "max_error": float(r[o + 2]), "count": int(round(r[o + 3]))}
+
+    return {"all_nodes": sub(0), "masked_nodes": sub(4)}
+
+
 def compute_metrics(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor | None = None,
                     log_scale: bool = True) -> dict:
     """MAE / RMSE / max error in the original scale for all and masked nodes (``model.py:156-216``).
-    Host-side numpy on purpose, exactly like the reference (not on the hot path)."""
+
+    CUDA tensors are reduced on the device by ``dfw_stress_metrics`` and only the 8 resulting numbers cross to the
+    host (the reference copies ``pred``/``target``/``mask`` in full, ``model.py:173-179``, once per validation batch,
+    ``train_gnn.py:85``); CPU tensors take the reference's numpy path verbatim.  ``metrics_from_device`` turns the
+    device result into the reference's dict, so callers can queue several batches and synchronise once."""
+    if pred.is_cuda and pred.dtype in (torch.float32, torch.bfloat16):
+        return metrics_from_device(ops.stress_metrics(pred, target, mask, log_scale))
     p = pred.detach().float().cpu().numpy().flatten()
     t = target.detach().float().cpu().numpy().flatten()
     m = mask.detach().cpu().numpy().flatten() if mask is not None else None

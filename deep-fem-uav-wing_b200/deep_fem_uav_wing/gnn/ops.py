@@ -340,6 +340,30 @@ def linear_bwd_weight(g_y, a1, a2=None, want_bias=True):
     return dw1, dw2, db
 
 
+def stress_metrics(pred, target, mask=None, log_scale=True) -> torch.Tensor:
+    """``dfw_stress_metrics``: 8 doubles on the device - [mae, rmse, max_error, count] for all nodes, then for the
+    masked nodes (``compute_metrics``, reference ``model.py:156-216``).  No host synchronisation."""
+    _require_cuda(pred, "pred")
+    p = pred.detach().contiguous()
+    t = target.detach().to(p.dtype).contiguous()
+    N = p.shape[0] if p.dim() > 0 else 1
+    C = p.numel() // max(N, 1) if N > 0 else 1
+    m = None
+    if mask is not None:
+        m = mask.detach().reshape(-1).contiguous()
+        m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+        if m.numel() != N:
+            raise ValueError(f"mask has {m.numel()} entries for {N} rows")
+    result = torch.empty(8, dtype=torch.float64, device=p.device)
+    ws_bytes = lib.dfw_stress_metrics_ws_bytes(N, C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
+    with torch.cuda.device(p.device), _prof("stress_metrics", 2 * N * C * _esz(p) + (N if m is not None else 0)):
+        check(lib.dfw_stress_metrics(p.data_ptr(), t.data_ptr(), _ptr(m), N, max(C, 1), int(bool(log_scale)), _dt(p),
+                                     result.data_ptr(), ws.data_ptr(), ws_bytes, _stream(p)))
+    LAUNCH_COUNTER["kernels"] += 1
+    return result
+
+
 def cast(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if t.dtype == dtype:
         return t.contiguous()

@@ -60,23 +60,34 @@ def train_epoch(model, loader, optimizer, criterion, device, ddp=None):
 
 @torch.no_grad()
 def evaluate(model, loader, criterion, device, log_scale=True):
-    """Mean loss and per-batch-averaged metrics (``train_gnn.py:66-109``)."""
+    """Mean loss and per-batch-averaged metrics (``train_gnn.py:66-109``).
+
+    Same numbers as the reference's loop, but nothing synchronises inside it: the per-batch loss and the 8 metric
+    statistics (``dfw_stress_metrics``) stay on the device and ONE copy at the end brings them all back (the
+    reference does ``loss.item()`` and three full D2H copies per batch, ``train_gnn.py:80,85``)."""
+    from deep_fem_uav_wing.gnn import ops
+
     model.eval()
-    total_loss, n_samples = 0.0, 0
-    acc = {k: {"mae": [], "rmse": [], "max_error": []} for k in ("all_nodes", "masked_nodes")}
+    losses, stats, counts = [], [], []
     for data in loader:
         data = data.to(device)
         out = model(data.x, data.edge_index, data.batch)
-        loss = criterion(out, data.y, data.loss_mask)
-        total_loss += loss.item() * data.num_graphs
-        n_samples += data.num_graphs
-        m = compute_metrics(out, data.y, data.loss_mask, log_scale=log_scale)
-        for k in acc:
-            for kk in acc[k]:
-                acc[k][kk].append(m[k][kk])
-    avg_loss = total_loss / n_samples if n_samples else 0.0
-    avg = {k: {"mae": sum(v["mae"]) / len(v["mae"]) if v["mae"] else 0.0, "rmse": sum(v["rmse"]) / len(v["rmse"]) if v["rmse"] else 0.0,
-               "max_error": max(v["max_error"]) if v["max_error"] else 0.0} for k, v in acc.items()}
+        losses.append(criterion(out, data.y, data.loss_mask).detach().double().reshape(1))
+        stats.append(ops.stress_metrics(out, data.y, data.loss_mask, log_scale=log_scale))
+        counts.append(data.num_graphs)
+    if not counts:
+        zero = {"mae": 0.0, "rmse": 0.0, "max_error": 0.0}
+        return 0.0, {"all_nodes": dict(zero), "masked_nodes": dict(zero)}
+    host = torch.cat([torch.cat(losses), torch.cat(stats)]).cpu().tolist()  # the only synchronisation
+    nb = len(counts)
+    loss_v, st = host[:nb], host[nb:]
+    avg_loss = sum(l * c for l, c in zip(loss_v, counts)) / sum(counts)
+    avg = {}
+    for k, o in (("all_nodes", 0), ("masked_nodes", 4)):
+        mae = [st[8 * i + o] for i in range(nb)]
+        rmse = [st[8 * i + o + 1] for i in range(nb)]
+        mx = [st[8 * i + o + 2] for i in range(nb)]
+        avg[k] = {"mae": sum(mae) / nb, "rmse": sum(rmse) / nb, "max_error": max(mx)}
     return avg_loss, avg
 
 

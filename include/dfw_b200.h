@@ -163,6 +163,18 @@ int dfw_masked_mse_bwd(const void* pred, const void* target, const uint8_t* mask
                        const float* g_loss, int64_t N, int64_t C, int reduction_mean, int dtype,
                        void* g_pred, dfw_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Evaluation metrics on the device: compute_metrics (model.py:156-216) without the full
+ * D2H copies of model.py:173-179.  result (device, 8 doubles) =
+ *   [mae, rmse, max_error, count] over all N*C elements, then the same over rows with mask[row] != 0;
+ * log_scale != 0 applies expm1 to pred and target first (model.py:184-185); an empty subset reports zeros
+ * (model.py:194-195); mask == NULL makes both halves equal (model.py:207-210).  Deterministic.
+ * ---------------------------------------------------------------------------------------- */
+size_t dfw_stress_metrics_ws_bytes(int64_t N, int64_t C);
+int dfw_stress_metrics(const void* pred, const void* target, const uint8_t* mask, int64_t N, int64_t C,
+                       int log_scale, int dtype, double* result, void* ws, size_t ws_bytes,
+                       dfw_stream_t stream);
+
 /* dtype conversion helper (weights fp32 -> bf16 copies for the bf16 path) */
 int dfw_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, dfw_stream_t stream);
 

@@ -224,3 +224,31 @@ def test_masked_mse_matches_reference_fixture(ops):
             else:
                 strict = MaskedMSELoss(red, strict_empty=True)(pred, targ, mm)
                 assert strict.item() == 0.0 and strict.requires_grad and strict.grad_fn is None  # fresh leaf (model.py:147-149)
+
+
+@pytest.mark.parametrize("n", [0, 1, 50, 200003])
+@pytest.mark.parametrize("log_scale", [True, False])
+def test_stress_metrics_match_the_reference_formulas(ops, n, log_scale):
+    """dfw_stress_metrics vs the oracle's restatement of compute_metrics (reference model.py:156-216): all nodes,
+    masked nodes, no mask, all-False mask, empty input; fp32 tolerance 1e-5 (device expm1f vs numpy expm1)."""
+    from deep_fem_uav_wing.gnn.model import compute_metrics, metrics_from_device
+    from oracle.sage_oracle import compute_metrics_ref
+
+    rng = np.random.default_rng(n + int(log_scale))
+    pred = torch.from_numpy((rng.standard_normal((n, 1)) * 2.0 + 8.0).astype(np.float32))
+    targ = torch.from_numpy((rng.standard_normal((n, 1)) * 2.0 + 8.0).astype(np.float32))
+    masks = {"mask": torch.from_numpy(rng.random(n) > 0.3), "none": None, "allfalse": torch.zeros(n, dtype=torch.bool)}
+    for name, m in masks.items():
+        ref = compute_metrics_ref(pred, targ, m, log_scale=log_scale)
+        got = compute_metrics(pred.cuda(), targ.cuda(), m.cuda() if m is not None else None, log_scale=log_scale)
+        assert got.keys() == ref.keys()
+        for sub in ("all_nodes", "masked_nodes"):
+            assert got[sub]["count"] == ref[sub]["count"], (name, sub)
+            for k in ("mae", "rmse", "max_error"):
+                assert abs(got[sub][k] - ref[sub][k]) <= 1e-5 * max(abs(ref[sub][k]), 1e-30) + 1e-12, (name, sub, k, got[sub][k], ref[sub][k])
+    # deterministic, and the device result converts to the same dict
+    if n:
+        a = ops.stress_metrics(pred.cuda(), targ.cuda(), masks["mask"].cuda(), log_scale)
+        b = ops.stress_metrics(pred.cuda(), targ.cuda(), masks["mask"].cuda(), log_scale)
+        assert torch.equal(a, b)
+        assert metrics_from_device(a) == compute_metrics(pred.cuda(), targ.cuda(), masks["mask"].cuda(), log_scale=log_scale)
