@@ -259,10 +259,20 @@ extern "C" size_t dfw_csr_ws_bytes(int64_t E, int64_t N) {
     return dfw::carve(nullptr, E, N).bytes;
 }
 
+namespace dfw {
+static int csr_build_impl(const int64_t* edge_index, int64_t E, int64_t N, int by_src, int32_t* rowptr, int32_t* col,
+                          int32_t* perm, float* inv_deg, int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
+}
+
 extern "C" int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src, int32_t* rowptr,
                              int32_t* col, int32_t* perm, float* inv_deg, int32_t* status, void* ws,
                              size_t ws_bytes, dfw_stream_t stream) {
-    using namespace dfw;
+    return dfw::csr_build_impl(edge_index, E, N, by_src, rowptr, col, perm, inv_deg, status, ws, ws_bytes, stream);
+}
+
+namespace dfw {
+static int csr_build_impl(const int64_t* edge_index, int64_t E, int64_t N, int by_src, int32_t* rowptr, int32_t* col,
+                          int32_t* perm, float* inv_deg, int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream) {
     DFW_REQUIRE(E >= 0 && N >= 0, "dfw_csr_build: negative size (E=%lld, N=%lld)", (long long)E, (long long)N);
     DFW_REQUIRE(E < 2147483647LL && N < 2147483647LL, "dfw_csr_build: E and N must be < 2^31 (E=%lld, N=%lld)",
                 (long long)E, (long long)N);
@@ -302,5 +312,217 @@ extern "C" int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, in
         k_sort_rows_big<<<kNumSMs * 2, 256, 0, s>>>(rowptr, w.keys, col, perm, w.worklist, w.counters);
         DFW_LAUNCH_CHECK();
     }
+    return 0;
+}
+}  // namespace dfw
+
+// =============================================================================================
+// (f1) Graph construction from triangle faces, on the device.
+//
+// Replaces the Python set loop of _faces_to_edge_index (reference src/deep_fem_uav_wing/gnn/dataset.py:26-63):
+//   faces [F,3] of node IDS -> 0-based indices through node_id_to_idx (dataset.py:106), faces holding an unknown id
+//   are skipped (dataset.py:43-46), the three undirected edges of every face are de-duplicated (dataset.py:49-52)
+//   and emitted in both directions (dataset.py:55-58; a degenerate self pair (i,i) therefore appears twice).
+// Here: expand to directed pairs -> the canonical CSR build above (rows sorted) -> per-row unique -> scan -> fill.
+// Output is the CSR by destination the aggregation consumes, plus (optionally) the int64 edge_index in canonical
+// (dst, src) order - the same edge SET as the reference, whose own order is Python-set iteration order.
+// Integer work, bit-exact against oracle/sage_oracle.py:faces_to_edge_index_ref after canonical sorting.
+// =============================================================================================
+namespace dfw {
+namespace {
+
+// idx of `id` in the ascending array sorted_ids[0..N), or -1
+__device__ __forceinline__ int64_t find_id(const int64_t* __restrict__ sorted_ids, int64_t N, int64_t id) {
+    int64_t lo = 0, hi = N;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted_ids[mid] < id) lo = mid + 1; else hi = mid;
+    }
+    return (lo < N && sorted_ids[lo] == id) ? lo : -1;
+}
+
+// one thread per face: 6 directed pairs into pairs[0][6f..] (src) / pairs[1][6f..] (dst); skipped faces write -1
+__global__ void k_faces_expand(const int64_t* __restrict__ faces, int64_t F, const int64_t* __restrict__ sorted_ids,
+                               const int64_t* __restrict__ id_perm, int64_t N, int64_t* __restrict__ pairs,
+                               int32_t* __restrict__ status) {
+    int skipped = 0;
+    const int64_t E0 = 6 * F;
+    for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < F; f += (int64_t)gridDim.x * blockDim.x) {
+        int64_t v[3];
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int64_t id = faces[3 * f + k];
+            int64_t idx;
+            if (sorted_ids) {
+                idx = find_id(sorted_ids, N, id);
+                if (idx >= 0 && id_perm) idx = id_perm[idx];
+            } else {
+                idx = ((uint64_t)id < (uint64_t)N) ? id : -1;
+            }
+            v[k] = idx;
+            ok = ok && idx >= 0;
+        }
+        skipped += !ok;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int64_t a = ok ? v[k] : -1, b = ok ? v[(k + 1) % 3] : -1;
+            pairs[6 * f + 2 * k] = a;          pairs[E0 + 6 * f + 2 * k] = b;       // a -> b
+            pairs[6 * f + 2 * k + 1] = b;      pairs[E0 + 6 * f + 2 * k + 1] = a;   // b -> a
+        }
+    }
+    if (skipped) atomicAdd(&status[2], skipped);
+}
+
+// warp per row of the duplicate-holding CSR: cnt_plus1[r+1] = distinct columns (+1 if the row holds itself)
+__global__ void __launch_bounds__(256) k_unique_count(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
+                                                       int64_t N, int32_t* __restrict__ cnt_plus1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += warps) {
+        const int beg = rowptr0[row], end = rowptr0[row + 1];
+        int n = 0;
+        for (int base = beg; base < end; base += 32) {
+            const int i = base + lane;
+            bool first = false, self = false;
+            if (i < end) {
+                const int c = col0[i];
+                first = (i == beg) || (col0[i - 1] != c);
+                self = first && c == (int)row;
+            }
+            n += __popc(__ballot_sync(0xffffffffu, first)) + __popc(__ballot_sync(0xffffffffu, self));
+        }
+        if (lane == 0) cnt_plus1[row + 1] = n;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_unique_fill(const int32_t* __restrict__ rowptr0, const int32_t* __restrict__ col0,
+                                                      const int32_t* __restrict__ rowptr, int64_t N, int32_t* __restrict__ col,
+                                                      int64_t* __restrict__ edge_index, int64_t ei_stride) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += warps) {
+        const int beg = rowptr0[row], end = rowptr0[row + 1];
+        int out = rowptr[row];
+        for (int base = beg; base < end; base += 32) {
+            const int i = base + lane;
+            bool first = false, self = false;
+            int c = 0;
+            if (i < end) {
+                c = col0[i];
+                first = (i == beg) || (col0[i - 1] != c);
+                self = first && c == (int)row;
+            }
+            const unsigned mf = __ballot_sync(0xffffffffu, first), ms = __ballot_sync(0xffffffffu, self);
+            const unsigned below = (1u << lane) - 1u;
+            if (first) {
+                const int pos = out + __popc(mf & below) + __popc(ms & below);
+                const int copies = self ? 2 : 1;
+                for (int k = 0; k < copies; ++k) {
+                    col[pos + k] = c;
+                    if (edge_index) {
+                        edge_index[pos + k] = c;                    // source
+                        edge_index[ei_stride + pos + k] = row;      // destination
+                    }
+                }
+            }
+            out += __popc(mf) + __popc(ms);
+        }
+    }
+}
+
+__global__ void k_store_count(const int32_t* __restrict__ rowptr, int64_t N, int64_t* __restrict__ num_edges) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *num_edges = rowptr[N];
+}
+
+struct FacesWs {
+    int64_t* pairs;    // [2, 6F]
+    int32_t* rowptr0;  // [N+1]
+    int32_t* col0;     // [6F]
+    void* csr_ws;
+    size_t csr_ws_bytes;
+    size_t bytes;
+};
+FacesWs carve_faces(void* ws, int64_t F, int64_t N) {
+    FacesWs w;
+    const int64_t E0 = 6 * F;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += align_up(bytes, 256);
+        return o;
+    };
+    const size_t o_pairs = take(sizeof(int64_t) * 2 * (size_t)(E0 > 0 ? E0 : 1));
+    const size_t o_rp = take(sizeof(int32_t) * (size_t)(N + 1));
+    const size_t o_col = take(sizeof(int32_t) * (size_t)(E0 > 0 ? E0 : 1));
+    w.csr_ws_bytes = carve(nullptr, E0, N).bytes;
+    const size_t o_csr = take(w.csr_ws_bytes);
+    char* base = reinterpret_cast<char*>(ws);
+    w.pairs = reinterpret_cast<int64_t*>(base + o_pairs);
+    w.rowptr0 = reinterpret_cast<int32_t*>(base + o_rp);
+    w.col0 = reinterpret_cast<int32_t*>(base + o_col);
+    w.csr_ws = base + o_csr;
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace
+}  // namespace dfw
+
+extern "C" size_t dfw_faces_ws_bytes(int64_t F, int64_t N) {
+    if (F < 0 || N < 0) return 0;
+    return dfw::carve_faces(nullptr, F, N).bytes;
+}
+
+extern "C" int dfw_faces_to_csr(const int64_t* faces, int64_t F, const int64_t* sorted_ids, const int64_t* id_perm, int64_t N,
+                                int32_t* rowptr, int32_t* col, float* inv_deg, int64_t* edge_index, int64_t* num_edges,
+                                int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(F >= 0 && N >= 0, "dfw_faces_to_csr: negative size (F=%lld, N=%lld)", (long long)F, (long long)N);
+    DFW_REQUIRE(6 * F < 2147483647LL && N < 2147483647LL, "dfw_faces_to_csr: 6F and N must be < 2^31");
+    DFW_REQUIRE(rowptr && status && num_edges && (col || F == 0), "dfw_faces_to_csr: null output pointer");
+    DFW_REQUIRE(faces || F == 0, "dfw_faces_to_csr: null faces");
+    FacesWs w = carve_faces(ws, F, N);
+    DFW_REQUIRE(ws && ws_bytes >= w.bytes, "dfw_faces_to_csr: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t E0 = 6 * F;
+    const int threads = 256;
+    DFW_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * 3, s));
+    if (F > 0) {
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((F + threads - 1) / threads, (int64_t)kNumSMs * 16));
+        k_faces_expand<<<grid, threads, 0, s>>>(faces, F, sorted_ids, id_perm, N, w.pairs, status);
+        DFW_LAUNCH_CHECK();
+    }
+    // duplicate-holding CSR by destination (row 1 of `pairs`), columns sorted inside every row.  It clears
+    // status[0..1] itself: [0] then counts the 6 placeholder pairs of every skipped face, [2] (ours) the faces.
+    {
+        // csr_build_impl zeroes status[0..1] only; keep status[2]
+        const int rc = csr_build_impl(w.pairs, E0, N, 0, w.rowptr0, w.col0, nullptr, nullptr, status, w.csr_ws, w.csr_ws_bytes, stream);
+        if (rc) return rc;
+    }
+    DFW_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * (size_t)(N + 1), s));
+    const int64_t warps_per_block = threads / 32;
+    const int grid_r = (int)std::max<int64_t>(1, std::min<int64_t>((N + warps_per_block - 1) / warps_per_block, (int64_t)kNumSMs * 64));
+    if (N > 0 && F > 0) {
+        k_unique_count<<<grid_r, threads, 0, s>>>(w.rowptr0, w.col0, N, rowptr);
+        DFW_LAUNCH_CHECK();
+    }
+    // scan -> rowptr, inv_deg, max degree (reuses the CSR build's scan; its cursor/blocksums live in the CSR workspace)
+    CsrWs cw = carve(w.csr_ws, E0, N);
+    DFW_CUDA(cudaMemsetAsync(status + 1, 0, sizeof(int32_t), s));
+    const int64_t n1 = N + 1;
+    const int nblk = (int)((n1 + kScanChunk - 1) / kScanChunk);
+    k_scan_partial<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, cw.blocksums);
+    DFW_LAUNCH_CHECK();
+    k_scan_blocksums<<<1, kScanThreads, 0, s>>>(cw.blocksums, nblk);
+    DFW_LAUNCH_CHECK();
+    k_scan_apply<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, cw.blocksums, cw.cursor, inv_deg, status);
+    DFW_LAUNCH_CHECK();
+    if (N > 0 && F > 0) {
+        k_unique_fill<<<grid_r, threads, 0, s>>>(w.rowptr0, w.col0, rowptr, N, col, edge_index, E0);
+        DFW_LAUNCH_CHECK();
+    }
+    k_store_count<<<1, 32, 0, s>>>(rowptr, N, num_edges);
+    DFW_LAUNCH_CHECK();
     return 0;
 }

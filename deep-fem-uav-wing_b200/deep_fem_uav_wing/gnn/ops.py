@@ -122,6 +122,7 @@ class CSRGraph:
     rowptr_t: torch.Tensor | None = None
     col_t: torch.Tensor | None = None
     _pending: list = field(default_factory=list)
+    skipped_faces: torch.Tensor | None = None
 
     def transpose(self):
         if self.rowptr_t is None:
@@ -166,6 +167,55 @@ def csr_build_raw(edge_index: torch.Tensor, num_nodes: int, by_src: bool = False
                                 status.data_ptr(), ws.data_ptr(), ws_bytes, _stream(ei)))
     LAUNCH_COUNTER["kernels"] += 7 if E > 0 else 3
     return rowptr, col, perm, inv_deg, status
+
+
+def faces_to_graph(faces: torch.Tensor, num_nodes: int, node_ids: torch.Tensor | None = None, want_edge_index: bool = True):
+    """Triangle faces -> (CSRGraph, edge_index) on the device (``dfw_faces_to_csr``; reference
+    ``_faces_to_edge_index``, ``dataset.py:26-63``).
+
+    ``faces``: int64 [F,3] of node ids; ``node_ids``: int64 [N] ids in node order (``npz["node_id"]``,
+    ``dataset.py:94``), or None when the faces already hold 0-based indices.  One 8-byte D2H read (the edge count).
+    The returned ``edge_index`` is registered with the graph cache, so ``model(x, edge_index)`` does not rebuild."""
+    _require_cuda(faces, "faces")
+    if faces.dtype != torch.int64:
+        raise TypeError(f"faces must be int64, got {faces.dtype}")
+    f = faces.reshape(-1, 3).contiguous()
+    F, N, dev = int(f.shape[0]), int(num_nodes), f.device
+    if 6 * F >= 2**31 - 1 or N >= 2**31 - 1:
+        raise ValueError("dfw_b200 uses int32 CSR indices: 6F and N must be < 2^31")
+    sorted_ids = id_perm = None
+    if node_ids is not None:
+        ids = node_ids.to(device=dev, dtype=torch.int64).contiguous()
+        if ids.numel() != N:
+            raise ValueError(f"node_ids has {ids.numel()} entries for {N} nodes")
+        if N > 1 and not bool((ids[1:] > ids[:-1]).all()):  # Gmsh surface ids come sorted (fem.py:611); else sort once
+            sorted_ids, id_perm = torch.sort(ids)
+            id_perm = id_perm.contiguous()
+        else:
+            sorted_ids = ids
+    cap = max(6 * F, 1)
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(cap, dtype=torch.int32, device=dev)
+    inv_deg = torch.empty(N, dtype=torch.float32, device=dev)
+    ei = torch.empty(2, cap, dtype=torch.int64, device=dev) if want_edge_index else None
+    nedges = torch.zeros(1, dtype=torch.int64, device=dev)
+    status = torch.empty(3, dtype=torch.int32, device=dev)
+    ws_bytes = lib.dfw_faces_ws_bytes(F, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev), _prof("faces_to_csr", 24 * F + 4 * (N + 1)):
+        check(lib.dfw_faces_to_csr(f.data_ptr(), F, _ptr(sorted_ids), _ptr(id_perm), N, rowptr.data_ptr(), col.data_ptr(),
+                                   inv_deg.data_ptr(), _ptr(ei), nedges.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes,
+                                   _stream(f)))
+    LAUNCH_COUNTER["kernels"] += 13
+    E = int(nedges.item())
+    col = col[:E]
+    edge_index = ei[:, :E].contiguous() if ei is not None else None
+    g = CSRGraph(edge_index, N, E, rowptr, col, inv_deg, None, status[:2])
+    g.rowptr_t, g.col_t = rowptr, col  # both directions of every edge are present: the transpose is the graph itself
+    g.skipped_faces = status[2:3]
+    if edge_index is not None:
+        register_graph(edge_index, g)
+    return g, edge_index
 
 
 _CSR_CACHE: "OrderedDict[tuple, CSRGraph]" = OrderedDict()

@@ -63,6 +63,24 @@ int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src,
                   int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (f1) graph construction from triangle faces: _faces_to_edge_index (dataset.py:26-63) on the device.
+ *     faces int64 [F,3] of node IDS.  sorted_ids (nullable) = the node ids in ascending order, id_perm (nullable) =
+ *     index of sorted_ids[k] in the caller's node order (NULL = identity): the device form of node_id_to_idx
+ *     (dataset.py:106).  sorted_ids == NULL: faces already hold 0-based indices.  Faces holding an unknown id are
+ *     skipped (dataset.py:43-46); undirected edges are de-duplicated and emitted in both directions
+ *     (dataset.py:49-58; a self pair (i,i) appears twice, as there).
+ *     Outputs: CSR by destination rowptr int32 [N+1], col int32 [capacity 6F], inv_deg fp32 [N] (nullable),
+ *     edge_index int64 [2, 6F] (nullable; row 0 = source, row 1 = destination, canonical (dst,src) order, the first
+ *     *num_edges columns of each row are valid), num_edges int64 (device), status int32 [3] (device):
+ *     [0] = placeholder pairs dropped (6 per skipped face), [1] = max degree, [2] = skipped faces.
+ *     The graph is symmetric, so the same CSR serves the backward gather.
+ * ---------------------------------------------------------------------------------------- */
+size_t dfw_faces_ws_bytes(int64_t F, int64_t N);
+int dfw_faces_to_csr(const int64_t* faces, int64_t F, const int64_t* sorted_ids, const int64_t* id_perm, int64_t N,
+                     int32_t* rowptr, int32_t* col, float* inv_deg, int64_t* edge_index, int64_t* num_edges,
+                     int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * (b) deterministic segmented neighbour aggregation (no atomics):
  *        out[i,:] = (addend ? addend[i,:] : 0) + (row_scale ? row_scale[i] : 1) * sum_{k in row i} x[col[k],:]
  *     row_scale = inv_deg  -> PyG mean aggregation (SAGEConv aggr='mean', model.py:63);

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import TOL_BF16, TOL_FP32, rel_l2, rel_max
+from helpers import TOL_BF16, TOL_FP32, load_golden, rel_l2, rel_max
 from oracle import csr_aggregate_c, csr_oracle_c
 from oracle.sage_oracle import csr_oracle
 
@@ -252,3 +252,59 @@ def test_stress_metrics_match_the_reference_formulas(ops, n, log_scale):
         b = ops.stress_metrics(pred.cuda(), targ.cuda(), masks["mask"].cuda(), log_scale)
         assert torch.equal(a, b)
         assert metrics_from_device(a) == compute_metrics(pred.cuda(), targ.cuda(), masks["mask"].cuda(), log_scale=log_scale)
+
+
+def _faces_case(ops, faces_np, node_ids_np, n):
+    """device faces -> graph vs the oracle restatement of _faces_to_edge_index (+ the CSR oracle), bit-exact."""
+    from helpers import canon_edges
+    from oracle.sage_oracle import faces_to_edge_index_ref
+
+    ids = {int(v): i for i, v in enumerate(node_ids_np)} if node_ids_np is not None else {i: i for i in range(n)}
+    ref = canon_edges(faces_to_edge_index_ref(faces_np.tolist(), ids))
+    g, ei = ops.faces_to_graph(torch.from_numpy(faces_np.astype(np.int64)).reshape(-1, 3).cuda(), n,
+                               None if node_ids_np is None else torch.from_numpy(node_ids_np.astype(np.int64)).cuda())
+    assert ei.dtype == torch.int64 and tuple(ei.shape) == ref.shape
+    assert np.array_equal(ei.cpu().numpy(), ref)  # canonical (dst, src) order, same edge multiset as the reference
+    rowptr, col, _, inv = csr_oracle_c(ref, n)
+    assert torch.equal(g.rowptr.cpu(), torch.from_numpy(rowptr)) and torch.equal(g.col.cpu(), torch.from_numpy(col))
+    assert torch.equal(g.inv_deg.cpu(), torch.from_numpy(inv))
+    assert g.num_edges == ref.shape[1]
+    # the registered graph is what the model's lookup returns, and its transpose is itself (symmetric)
+    assert ops.get_graph(ei, n) is g and g.transpose()[1] is g.col
+    return g, ei
+
+
+def test_faces_to_graph_matches_reference_fixture_and_edge_cases(ops):
+    gold = load_golden("faces_to_edge_index")
+    faces = gold["faces"]  # the 12-triangle box of geometry.py:82-102 with node ids 10..17
+    ids = np.arange(10, 18)
+    g, ei = _faces_case(ops, faces, ids, 8)
+    assert ei.shape == (2, 36) and int(g.skipped_faces.item()) == 0
+    # a face touching an unknown id is skipped (dataset.py:43-46)
+    g2, ei2 = _faces_case(ops, np.concatenate([faces, [[10, 11, 999]]]), ids, 8)
+    assert torch.equal(ei2, ei) and int(g2.skipped_faces.item()) == 1
+    # node ids given in a scrambled order (mapping through the sort permutation)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(8)
+    _faces_case(ops, faces, ids[perm], 8)
+    # degenerate faces: repeated vertices give self pairs, which the reference emits twice
+    _faces_case(ops, np.array([[0, 0, 1], [2, 2, 2], [1, 3, 1]]), None, 5)
+    # empty
+    g0, ei0 = ops.faces_to_graph(torch.zeros(0, 3, dtype=torch.int64, device="cuda"), 4)
+    assert ei0.shape == (2, 0) and g0.rowptr.tolist() == [0, 0, 0, 0, 0]
+
+
+def test_faces_to_graph_on_a_config_sized_surface_mesh(ops):
+    """50k-node closed wing surface (config 2's mesh): same edge_index as the host construction, and the model's
+    forward on it equals the forward on the host-built edge_index."""
+    from helpers import canon_edges
+    from deep_fem_uav_wing.gnn import synth
+
+    m = synth.surface_tri_wing(50000, seed=42)
+    n = m["num_nodes"]
+    g, ei = _faces_case(ops, m["faces"], None, n)
+    assert np.array_equal(ei.cpu().numpy(), canon_edges(m["edge_index"]))
+    x = torch.randn(n, 64, device="cuda")
+    a = ops.aggregate(g.rowptr, g.col, g.inv_deg, x)
+    g_host = ops.get_graph(torch.from_numpy(m["edge_index"]).cuda(), n)
+    assert torch.equal(a, ops.aggregate(g_host.rowptr, g_host.col, g_host.inv_deg, x))
