@@ -127,6 +127,56 @@ def build_graph_data(surface_npz_path: Path, boundary_sets_path: Path, params_pa
     }
 
 
+def build_graph_data_device(surface_npz_path: Path, boundary_sets_path: Path, params_path: Path, *, device="cuda",
+                            log_scale_stress: bool = True, normalize_pos: bool = True) -> dict[str, Any]:
+    """``build_graph_data`` with the graph construction and the feature assembly on the GPU.
+
+    Same keys as :func:`build_graph_data`; ``x``, ``edge_index``, ``y``, ``loss_mask`` and ``pos`` are CUDA tensors
+    (``edge_index`` in canonical (dst, src) order with its CSR already registered, so the first forward does not
+    rebuild it), the rest stays numpy.  The host only parses the three files and copies the RAW arrays:
+    ``dfw_faces_to_csr`` replaces the Python set loop of ``_faces_to_edge_index`` (``dataset.py:26-63``) and
+    ``dfw_node_features`` the numpy block of ``dataset.py:129-151``."""
+    from . import ops
+
+    dev = torch.device(device)
+    npz = np.load(surface_npz_path)
+    boundary_sets = json.loads(Path(boundary_sets_path).read_text(encoding="utf-8"))
+    params = json.loads(Path(params_path).read_text(encoding="utf-8"))
+    node_ids = np.asarray(npz["node_id"], dtype=np.int64)
+    n = len(node_ids)
+    if n > 1 and np.unique(node_ids).size != n:  # duplicate ids (last one wins in the reference's dict): host path
+        g = build_graph_data(surface_npz_path, boundary_sets_path, params_path, log_scale_stress=log_scale_stress,
+                             normalize_pos=normalize_pos)
+        for k in ("x", "edge_index", "y", "loss_mask", "pos"):
+            g[k] = torch.from_numpy(np.asarray(g[k])).to(dev)
+        return g
+    pos = npz["pos"].astype(np.float32)
+    stress_vm = npz["stress_vm"].astype(np.float32)
+    faces = np.asarray(boundary_sets["surf_all_faces"], dtype=np.int64).reshape(-1, 3)
+    span_m, chord_m = params["span_m"], params["chord_m"]
+    sweep_deg, thickness_ratio = params["sweep_deg"], params["thickness_ratio"]
+    global_params = np.array(
+        [(span_m - 1.0) / 1.0, (chord_m - 0.2) / 0.3, sweep_deg / 30.0, (thickness_ratio - 0.05) / 0.10], dtype=np.float32
+    )
+    pos_d = torch.from_numpy(pos).to(dev, non_blocking=True)
+    x, y = ops.node_features(pos_d, torch.from_numpy(npz["normal"].astype(np.float32)).to(dev, non_blocking=True),
+                             torch.from_numpy(stress_vm).to(dev, non_blocking=True), global_params,
+                             normalize_pos=normalize_pos, log_scale=log_scale_stress)
+    _, edge_index = ops.faces_to_graph(torch.from_numpy(faces).to(dev, non_blocking=True), n, torch.from_numpy(node_ids).to(dev))
+    return {
+        "x": x,
+        "edge_index": edge_index,
+        "y": y,
+        "loss_mask": torch.from_numpy(npz["loss_mask"].astype(bool)).to(dev),
+        "pos": pos_d,
+        "disp": npz["disp"].astype(np.float32),
+        "stress_vm_raw": stress_vm,
+        "case_id": params["case_id"],
+        "global_params": global_params,
+        "global_params_raw": np.array([span_m, chord_m, sweep_deg, thickness_ratio], dtype=np.float32),
+    }
+
+
 def graph_dict_to_data(g: dict) -> Data:
     return Data(
         x=torch.from_numpy(g["x"]), edge_index=torch.from_numpy(g["edge_index"]), y=torch.from_numpy(g["y"]),

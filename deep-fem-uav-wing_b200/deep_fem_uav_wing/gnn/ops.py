@@ -218,6 +218,30 @@ def faces_to_graph(faces: torch.Tensor, num_nodes: int, node_ids: torch.Tensor |
     return g, edge_index
 
 
+def node_features(pos: torch.Tensor, normal: torch.Tensor, stress: torch.Tensor | None, global_params, normalize_pos=True,
+                  log_scale=True):
+    """``dfw_node_features``: x [N,10] and y [N,1] of ``build_graph_data`` (``dataset.py:129-151``) on the device."""
+    import ctypes
+
+    _require_cuda(pos, "pos")
+    pos = pos.to(torch.float32).contiguous()
+    normal = normal.to(torch.float32).contiguous()
+    N, dev = int(pos.shape[0]), pos.device
+    x = torch.empty(N, 10, dtype=torch.float32, device=dev)
+    y = None
+    if stress is not None:
+        stress = stress.to(torch.float32).contiguous()
+        y = torch.empty(N, 1, dtype=torch.float32, device=dev)
+    gp = (ctypes.c_float * 4)(*[float(v) for v in global_params])
+    ws_bytes = lib.dfw_node_features_ws_bytes(N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev), _prof("node_features", 72 * N):
+        check(lib.dfw_node_features(pos.data_ptr(), normal.data_ptr(), _ptr(stress), gp, int(bool(normalize_pos)), int(bool(log_scale)),
+                                    x.data_ptr(), _ptr(y), N, ws.data_ptr(), ws_bytes, _stream(pos)))
+    LAUNCH_COUNTER["kernels"] += 2
+    return x, y
+
+
 _CSR_CACHE: "OrderedDict[tuple, CSRGraph]" = OrderedDict()
 _CSR_CACHE_SIZE = 64
 

@@ -80,6 +80,15 @@ int dfw_faces_to_csr(const int64_t* faces, int64_t F, const int64_t* sorted_ids,
                      int32_t* rowptr, int32_t* col, float* inv_deg, int64_t* edge_index, int64_t* num_edges,
                      int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
 
+/* Node features of build_graph_data (dataset.py:129-151) on the device:
+ *   x [N,10] fp32 = [(pos - min)/range | normal/|normal| | global_params4], y [N,1] fp32 = log1p(stress) (nullable).
+ *   pos, normal fp32 [N,3], stress fp32 [N] on the device; global_params4 = 4 HOST floats (dataset.py:122-127).
+ *   x is bit-identical to the reference's numpy float32 arithmetic; y may differ in the last ulp (log1pf). */
+size_t dfw_node_features_ws_bytes(int64_t N);
+int dfw_node_features(const float* pos, const float* normal, const float* stress, const float* global_params4,
+                      int normalize_pos, int log_scale, float* x, float* y, int64_t N, void* ws, size_t ws_bytes,
+                      dfw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (b) deterministic segmented neighbour aggregation (no atomics):
  *        out[i,:] = (addend ? addend[i,:] : 0) + (row_scale ? row_scale[i] : 1) * sum_{k in row i} x[col[k],:]

@@ -289,3 +289,44 @@ def test_cuda_graph_training_step_matches_eager():
     with torch.no_grad():
         for x, ei, _, _ in batches[:3]:
             assert rel_max(gf(x, ei), model(x, ei)) < TOL_FP32
+
+
+@pytest.mark.gpu
+def test_build_graph_data_device_matches_reference_fixture():
+    """build_graph_data_device (dfw_node_features + dfw_faces_to_csr) vs the fixture written by the reference's own
+    dataset.py (tests/golden/make_golden.py): x bit-identical, y within 2 ulp (log1pf), same edge set, and a synthetic
+    50k-node case against the host construction."""
+    import json
+    import tempfile
+    from pathlib import Path
+
+    from helpers import canon_edges
+    from test_dataset_golden import _write_case
+
+    from deep_fem_uav_wing.gnn import synth
+    from deep_fem_uav_wing.gnn.dataset import build_graph_data, build_graph_data_device
+
+    g = load_golden("build_graph_case")
+    with tempfile.TemporaryDirectory() as td:
+        cid, raw = _write_case(g, td)
+        paths = (raw / "fem" / cid / "surface_results.npz", raw / "mesh" / cid / "boundary_sets.json", raw / "geometry" / cid / "params.json")
+        got = build_graph_data_device(*paths)
+    assert got["x"].is_cuda and got["x"].dtype == torch.float32 and got["edge_index"].dtype == torch.int64
+    assert np.array_equal(got["x"].cpu().numpy(), g["x"])  # bit-identical to the reference's numpy float32 arithmetic
+    y = got["y"].cpu().numpy()
+    assert y.shape == g["y"].shape and np.all(np.abs(y - g["y"]) <= 2 * np.spacing(np.abs(g["y"])))
+    assert np.array_equal(got["loss_mask"].cpu().numpy(), g["loss_mask"]) and np.array_equal(got["pos"].cpu().numpy(), g["pos"])
+    for k in ("stress_vm_raw", "global_params", "global_params_raw"):
+        assert np.array_equal(got[k], g[k]), k
+    assert np.array_equal(got["edge_index"].cpu().numpy(), canon_edges(g["edge_index"]))
+    # synthetic config-2 mesh written in the reference's three-file case format
+    m = synth.surface_tri_wing(50000, seed=7)
+    with tempfile.TemporaryDirectory() as td:
+        cid = synth.write_case_files(m, Path(td), node_id_base=1)
+        raw = Path(td) / "data" / "raw"
+        paths = (raw / "fem" / cid / "surface_results.npz", raw / "mesh" / cid / "boundary_sets.json", raw / "geometry" / cid / "params.json")
+        host = build_graph_data(*paths)
+        dev = build_graph_data_device(*paths)
+    assert np.array_equal(dev["x"].cpu().numpy(), host["x"])
+    assert np.all(np.abs(dev["y"].cpu().numpy() - host["y"]) <= 2 * np.spacing(np.abs(host["y"])))
+    assert np.array_equal(dev["edge_index"].cpu().numpy(), canon_edges(host["edge_index"]))
