@@ -20,7 +20,7 @@ sys.path.insert(0, str(PKG_ROOT))
 
 import torch  # noqa: E402
 
-from deep_fem_uav_wing.gnn.dataset import build_graph_data  # noqa: E402
+from deep_fem_uav_wing.gnn.dataset import build_graph_data, build_graph_data_device  # noqa: E402
 from deep_fem_uav_wing.gnn.glb import hot_rgb, viridis_rgb, write_glb  # noqa: E402
 from deep_fem_uav_wing.gnn.model import GraphSAGEModel, compute_metrics  # noqa: E402
 
@@ -50,11 +50,10 @@ def run_inference(model, case_id: str, device, paths: dict, *, log_scale_stress:
     for q, name in ((npz_p, "surface_results.npz"), (bs_p, "boundary_sets.json"), (par_p, "params.json")):
         if not q.exists():
             return {"status": "failed", "reason": f"{name} not found"}
-    g = build_graph_data(npz_p, bs_p, par_p, log_scale_stress=log_scale_stress, normalize_pos=True)
-    x = torch.from_numpy(g["x"]).to(device)
-    edge_index = torch.from_numpy(g["edge_index"]).to(device)
-    y = torch.from_numpy(g["y"]).to(device)
-    loss_mask = torch.from_numpy(g["loss_mask"]).to(device)
+    # graph construction (faces -> CSR) and feature assembly run on the GPU (dfw_faces_to_csr, dfw_node_features)
+    g = build_graph_data_device(npz_p, bs_p, par_p, device=device, log_scale_stress=log_scale_stress, normalize_pos=True)
+    x, edge_index, y, loss_mask = g["x"], g["edge_index"], g["y"], g["loss_mask"]
+    g["loss_mask"] = loss_mask.cpu().numpy()
     with torch.no_grad():
         pred_log = model(x, edge_index)
     metrics = compute_metrics(pred_log, y, loss_mask, log_scale=log_scale_stress)

@@ -158,6 +158,55 @@ def cfg5(n_meshes):
         dist.destroy_process_group()
 
 
+def graph_build():
+    """graph construction from faces + feature assembly, and the evaluation metrics, device vs host.
+    Host arms: the oracle's restatement of the reference's Python set loop (dataset.py:26-63), and this package's
+    vectorised numpy path; all on the same 50k-node closed wing surface (config 2's mesh)."""
+    from deep_fem_uav_wing.gnn.dataset import _faces_to_edge_index
+    from deep_fem_uav_wing.gnn.model import compute_metrics
+    from oracle.sage_oracle import compute_metrics_ref, faces_to_edge_index_ref
+
+    m = synth.surface_tri_wing(50000, seed=42)
+    n, faces = m["num_nodes"], m["faces"].astype(np.int64)
+    ids = {i: i for i in range(n)}
+    t0 = time.perf_counter(); ref = faces_to_edge_index_ref(faces.tolist(), ids); t_loop = time.perf_counter() - t0
+    t0 = time.perf_counter(); _faces_to_edge_index(faces, ids); t_np = time.perf_counter() - t0
+    fd = torch.from_numpy(faces).cuda()
+    med, p10, p90 = gpu_time(lambda: ops.faces_to_graph(fd, n), iters=10, flush=False)  # includes the 8-byte edge-count read
+    ops.clear_graph_cache()
+    t0 = time.perf_counter()
+    eid = torch.from_numpy(ref).cuda()
+    ops.get_graph(eid, n)
+    torch.cuda.synchronize()
+    t_h2d_csr = time.perf_counter() - t0
+    pos, nrm, st = (torch.from_numpy(m[k].astype(np.float32)).cuda() for k in ("pos", "normal", "stress_vm_raw"))
+    fmed, _, _ = gpu_time(lambda: ops.node_features(pos, nrm, st, [0.1, 0.2, 0.3, 0.4]), iters=20, flush=False)
+    pred, targ = torch.from_numpy(m["y"]) + 0.01, torch.from_numpy(m["y"])
+    mask = torch.from_numpy(m["loss_mask"])
+    t0 = time.perf_counter()
+    for _ in range(5):
+        compute_metrics_ref(pred, targ, mask)
+    t_met_host = (time.perf_counter() - t0) / 5
+    pd, td, md = pred.cuda(), targ.cuda(), mask.cuda()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        compute_metrics_ref(pd, td, md)  # the reference's path on CUDA tensors: three full D2H copies + numpy
+    t_met_ref_cuda = (time.perf_counter() - t0) / 5
+    mmed, _, _ = gpu_time(lambda: ops.stress_metrics(pd, td, md), iters=20, flush=False)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        compute_metrics(pd, td, md)
+    t_met_dev_e2e = (time.perf_counter() - t0) / 20
+    print(json.dumps({"config": "graph_build (8f-1, 8f-2)", "N": n, "F": int(faces.shape[0]), "E": int(ref.shape[1]),
+                      "faces_to_edge_index_python_set_loop_ms": round(t_loop * 1e3, 2), "faces_to_edge_index_numpy_ms": round(t_np * 1e3, 2),
+                      "host_edge_index_h2d_plus_csr_build_ms": round(t_h2d_csr * 1e3, 3),
+                      "faces_to_csr_device_us": round(med * 1e6, 1), "faces_to_csr_p10_p90_us": [round(p10 * 1e6, 1), round(p90 * 1e6, 1)],
+                      "node_features_device_us": round(fmed * 1e6, 1),
+                      "metrics_reference_numpy_cpu_tensors_ms": round(t_met_host * 1e3, 3),
+                      "metrics_reference_path_cuda_tensors_ms": round(t_met_ref_cuda * 1e3, 3),
+                      "metrics_device_kernel_us": round(mmed * 1e6, 1), "metrics_device_incl_d2h_dict_ms": round(t_met_dev_e2e * 1e3, 3)}), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "cfg1"
     if what == "cfg1":
@@ -166,3 +215,5 @@ if __name__ == "__main__":
         cfg4()
     elif what == "cfg5":
         cfg5(int(sys.argv[2]) if len(sys.argv) > 2 else 1250)
+    elif what == "graph":
+        graph_build()
