@@ -12,8 +12,8 @@ latency-bound over NVLink/NVSwitch.  Design:
 * ``finish()`` waits for the buckets before the optimizer step;
 * ``scale_loss`` reproduces the single-process loss of the union batch exactly: the reference's
   ``MaskedMSELoss`` is a mean over the masked nodes of the WHOLE batch (``model.py:151``), so each
-  rank's mean is re-weighted by ``count_r * world / sum(count)`` before backward and the averaged
-  gradients equal the single-process ones.
+  rank back-propagates its SUM of squared errors (``loss_r * count_r``), the counts are all-reduced
+  asynchronously next to the gradients, and ``finish()`` divides by the total count.
 Works with any backend (NCCL on GPUs; gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -56,6 +56,7 @@ class MeshDataParallel(nn.Module):
         for p in order:
             self._count[self._bucket_of[id(p)]] += 1
         self._handles: list = []
+        self._tot, self._tot_handle = None, None
         self._reset()
         if self.world > 1:
             # identical initial weights on every rank
@@ -85,13 +86,17 @@ class MeshDataParallel(nn.Module):
         self.flat.zero_()
 
     def scale_loss(self, loss: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
-        """loss_r (a mean over count_r elements) -> loss_r * count_r * world / sum_r count_r."""
+        """``loss_r`` (a mean over ``count_r`` masked elements) -> the quantity to call ``backward()`` on.
+
+        Returns ``loss_r * count_r`` (this rank's SUM of squared errors) and starts an asynchronous all-reduce of the
+        count; ``finish()`` divides the summed gradients by the summed count, which is exactly the gradient of the
+        mean over the union batch (``model.py:151``).  Nothing waits between forward and backward: the count travels
+        while the backward runs (a blocking all-reduce here was a synchronisation point of all ranks mid-step)."""
         if self.world == 1:
             return loss
-        tot = count.detach().clone().float().reshape(1)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.pg)
-        w = count.detach().float() * float(self.world) / tot.clamp_min(1.0)
-        return loss * w.reshape(())
+        self._tot = count.detach().clone().float().reshape(1)
+        self._tot_handle = dist.all_reduce(self._tot, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        return loss * count.detach().float().reshape(())
 
     def finish(self):
         """Call after ``backward()`` and before ``optimizer.step()``."""
@@ -105,5 +110,10 @@ class MeshDataParallel(nn.Module):
                         self._launch(b)
             for h in self._handles:
                 h.wait()
-            self.flat.div_(self.world)
+            if self._tot_handle is not None:  # gradients of per-rank SUMS -> gradient of the union-batch mean
+                self._tot_handle.wait()
+                self.flat.div_(self._tot.clamp_min(1.0))
+                self._tot_handle = None
+            else:  # scale_loss was not used: plain average of the ranks' gradients
+                self.flat.div_(self.world)
         self._reset()
