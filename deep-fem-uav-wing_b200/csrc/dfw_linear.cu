@@ -439,17 +439,25 @@ __global__ void __launch_bounds__(kThreads) k_linear(const LinArgs p) {
     }
 }
 
-// second pass of dW: fixed-order sum over splits
+// second pass of dW: fixed-order sum over splits.  A block of 8 warps owns 32 consecutive outputs (one per lane, so
+// every load is a coalesced 128-byte row segment of a partial tile); warp w sums splits w, w+8, w+16, ... and the
+// eight partial sums are added in warp order.  (One thread per output walking all ~146 splits was a 15 us
+// dependent-load chain for 19 MB of L2-resident partials.)
+constexpr int kDwRedWarps = 8;
 template <int BM, int BN>
-__global__ void k_dw_reduce(const float* __restrict__ part, const float* __restrict__ part_db, int splits, int tiles_i,
-                            int tiles_j1, int tiles_j2, int64_t Hout, int64_t k1, int64_t k2, float* __restrict__ dw1,
-                            float* __restrict__ dw2, float* __restrict__ dbias, int accumulate) {
+__global__ void __launch_bounds__(kDwRedWarps * 32) k_dw_reduce(const float* __restrict__ part, const float* __restrict__ part_db, int splits,
+                                                                int tiles_i, int tiles_j1, int tiles_j2, int64_t Hout, int64_t k1, int64_t k2,
+                                                                float* __restrict__ dw1, float* __restrict__ dw2, float* __restrict__ dbias,
+                                                                int accumulate) {
+    __shared__ float red[kDwRedWarps][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t n1 = Hout * k1, n2 = Hout * k2;
     const int64_t total = n1 + n2 + (dbias ? Hout : 0);
     const int tiles = tiles_i * (tiles_j1 + tiles_j2);
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+        const int64_t idx = base + lane;
         float s = 0.f;
-        float* dst;
+        float* dst = nullptr;
         if (idx < n1 + n2) {
             const bool second = idx >= n1;
             const int64_t e = second ? idx - n1 : idx;
@@ -457,27 +465,33 @@ __global__ void k_dw_reduce(const float* __restrict__ part, const float* __restr
             const int64_t i = e / k, j = e % k;
             const int ti = (int)(i / BM), tj = (int)(j / BN) + (second ? tiles_j1 : 0);
             const int64_t off = (int64_t)(ti * (tiles_j1 + tiles_j2) + tj) * (BM * BN) + (i % BM) * BN + (j % BN);
-            {  // four interleaved partial sums (fixed order): keeps 4 loads in flight instead of a dependent chain
-                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-                const int64_t st = (int64_t)tiles * (BM * BN);
-                int sp = 0;
-                for (; sp + 3 < splits; sp += 4) {
-                    q0 += part[(int64_t)sp * st + off];
-                    q1 += part[(int64_t)(sp + 1) * st + off];
-                    q2 += part[(int64_t)(sp + 2) * st + off];
-                    q3 += part[(int64_t)(sp + 3) * st + off];
-                }
-                for (; sp < splits; ++sp) q0 += part[(int64_t)sp * st + off];
-                s = (q0 + q1) + (q2 + q3);
+            const int64_t st = (int64_t)tiles * (BM * BN);
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;  // four loads in flight, fixed association
+            int sp = w;
+            for (; sp + 3 * kDwRedWarps < splits; sp += 4 * kDwRedWarps) {
+                q0 += part[(int64_t)sp * st + off];
+                q1 += part[(int64_t)(sp + kDwRedWarps) * st + off];
+                q2 += part[(int64_t)(sp + 2 * kDwRedWarps) * st + off];
+                q3 += part[(int64_t)(sp + 3 * kDwRedWarps) * st + off];
             }
+            for (; sp < splits; sp += kDwRedWarps) q0 += part[(int64_t)sp * st + off];
+            s = (q0 + q1) + (q2 + q3);
             dst = (second ? dw2 : dw1) + e;
-        } else {
+        } else if (idx < total) {
             const int64_t i = idx - n1 - n2;
             const int ti = (int)(i / BM);
-            for (int sp = 0; sp < splits; ++sp) s += part_db[((int64_t)sp * tiles_i + ti) * BM + (i % BM)];
+            for (int sp = w; sp < splits; sp += kDwRedWarps) s += part_db[((int64_t)sp * tiles_i + ti) * BM + (i % BM)];
             dst = dbias + i;
         }
-        *dst = accumulate ? *dst + s : s;
+        red[w][lane] = s;
+        __syncthreads();
+        if (w == 0 && dst) {
+            float t = red[0][lane];
+#pragma unroll
+            for (int k = 1; k < kDwRedWarps; ++k) t += red[k][lane];
+            *dst = accumulate ? *dst + t : t;
+        }
+        __syncthreads();
     }
 }
 
@@ -743,8 +757,8 @@ extern "C" int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1
         if (rc) return rc;
         if (dbias && (rc = colsum_launch(g_y, N, Hout, dtype, part_db, dbias, accumulate, s))) return rc;
         const int64_t total = Hout * (k1 + k2);
-        const int rgrid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 8);
-        k_dw_reduce<128, 128><<<rgrid, 256, 0, s>>>(part, nullptr, pt.splits, pt.tiles_i, pt.tiles_j1, pt.tiles_j2, Hout, k1, k2, dw1,
+        const int rgrid = (int)std::min<int64_t>((total + 31) / 32, (int64_t)kNumSMs * 8);
+        k_dw_reduce<128, 128><<<rgrid, kDwRedWarps * 32, 0, s>>>(part, nullptr, pt.splits, pt.tiles_i, pt.tiles_j1, pt.tiles_j2, Hout, k1, k2, dw1,
                                                     dw2, nullptr, accumulate);
         DFW_LAUNCH_CHECK();
         return 0;
@@ -786,8 +800,8 @@ extern "C" int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1
     }
     if (rc) return rc;
     const int64_t total = Hout * (k1 + k2) + (dbias ? Hout : 0);
-    const int rgrid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 8);
-    k_dw_reduce<DW_BM, DW_BN><<<rgrid, 256, 0, s>>>(a.part, a.part_db, a.splits, pl.tiles_i, pl.tiles_j1, pl.tiles_j2, Hout,
+    const int rgrid = (int)std::min<int64_t>((total + 31) / 32, (int64_t)kNumSMs * 8);
+    k_dw_reduce<DW_BM, DW_BN><<<rgrid, kDwRedWarps * 32, 0, s>>>(a.part, a.part_db, a.splits, pl.tiles_i, pl.tiles_j1, pl.tiles_j2, Hout,
                                                     k1, k2, dw1, dw2, dbias, accumulate);
     DFW_LAUNCH_CHECK();
     return 0;
