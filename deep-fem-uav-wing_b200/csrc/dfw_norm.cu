@@ -59,7 +59,11 @@ struct EbArgs {
     int64_t N; int H; int flags;
 };
 
-template <typename T, int VPL>
+// SPEC = 0: every option is a run-time flag.  SPEC = 1 / 3: the SAGE layer's tail (LayerNorm + ReLU, gradient from
+// g_out; bit 1 = dropout) with the options folded at compile time - the generic kernel is issue bound (250 warp
+// instructions per row, 63 % issue utilisation at 25 % occupancy, profiles/r01_ncu_summary_final.txt) and a good
+// part of that was flag tests and the never-taken rowdot / act paths inside the row loop.
+template <typename T, int VPL, int SPEC>
 __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(const EbArgs p) {
     constexpr int kMaxVPL = VPL;  // 16-byte column groups per lane: 1 (H <= 128) or 2 (H <= 256)
     __shared__ float red[kEbWarps][3][256 + 1];
@@ -67,11 +71,13 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int H = p.H;
     const float invH = 1.f / (float)H;
-    const bool ln = p.flags & DFW_EP_LAYERNORM, relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
+    const bool ln = SPEC ? true : (bool)(p.flags & DFW_EP_LAYERNORM), relu = SPEC ? true : (bool)(p.flags & DFW_EP_RELU);
+    const bool drop = SPEC ? (bool)(SPEC & 2) : (bool)(p.flags & DFW_EP_DROPOUT);
+    const bool has_rowdot = SPEC ? false : p.g_rowdot != nullptr;
     const uint64_t seed_v = drop ? resolve_seed(p.seed, p.flags) : 0ull;
     const T* gout = (const T*)p.g_out;
     const T* pre = (const T*)p.pre_out;
-    const T* act = (const T*)p.act;
+    const T* act = SPEC ? nullptr : (const T*)p.act;
     T* gy = (T*)p.g_y;
 
     float gam[kMaxVPL][4], bet[kMaxVPL][4], rdw[kMaxVPL][4];
@@ -116,12 +122,12 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
                     mean[r] = __ldg(p.ln_stats + 2 * row);
                     rstd[r] = __ldg(p.ln_stats + 2 * row + 1);
                 }
-                if (p.g_rowdot) gr[r] = __ldg(p.g_rowdot + row);
+                if (has_rowdot) gr[r] = __ldg(p.g_rowdot + row);
 #pragma unroll
                 for (int v = 0; v < kMaxVPL; ++v) {
                     if (!vok[v]) continue;
                     const int64_t off = row * H + (lane + v * 32) * 4;
-                    if (!p.g_rowdot) ld4(gout + off, g[r][v]);
+                    if (!has_rowdot) ld4(gout + off, g[r][v]);
                     if (ln) ld4(pre + off, y[r][v]);
                     else if (act) ld4(act + off, y[r][v]);
                 }
@@ -131,14 +137,14 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
         for (int r = 0; r < kR; ++r) {
             if (!rv[r]) continue;  // warp-uniform
             const int64_t row = row0 + r;
-            if (p.g_rowdot && lane == 0) sum_gr += gr[r];
+            if (has_rowdot && lane == 0) sum_gr += gr[r];
             float xh[kMaxVPL][4];
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int v = 0; v < kMaxVPL; ++v) {
                 if (!vok[v]) continue;
                 const int64_t off = row * H + (lane + v * 32) * 4;
-                if (p.g_rowdot) {
+                if (has_rowdot) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) g[r][v][j] = gr[r] * rdw[v][j];
                 }
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float a = act ? y[r][v][j] : 1.f;
-                        if (p.g_rowdot) c0[v][j] += gr[r] * (a * keep[j]);  // d_rowdot_w (a is post-ReLU)
+                        if (has_rowdot) c0[v][j] += gr[r] * (a * keep[j]);  // d_rowdot_w (a is post-ReLU)
                         float gg = g[r][v][j] * keep[j];
                         if (relu && !(a > 0.f)) gg = 0.f;
                         g[r][v][j] = gg;
@@ -363,13 +369,23 @@ extern "C" int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const 
     a.g_y = g_y; a.part = need_cols ? reinterpret_cast<float*>(ws) : nullptr;
     a.N = N; a.H = (int)Hout; a.flags = flags;
     if (N > 0) {
+        // the SAGE layer's tail gets the specialised instantiation
+        const bool tail = ln && (flags & DFW_EP_RELU) && g_out && !g_rowdot;
+        const int spec = tail ? ((flags & DFW_EP_DROPOUT) ? 3 : 1) : 0;
+#define DFW_EB_GO(TT, V)                                                                     \
+    do {                                                                                     \
+        if (spec == 3) k_epilogue_bwd<TT, V, 3><<<blocks, kEbThreads, 0, s>>>(a);            \
+        else if (spec == 1) k_epilogue_bwd<TT, V, 1><<<blocks, kEbThreads, 0, s>>>(a);       \
+        else k_epilogue_bwd<TT, V, 0><<<blocks, kEbThreads, 0, s>>>(a);                      \
+    } while (0)
         if (Hout <= 128) {
-            if (dtype == DFW_F32) k_epilogue_bwd<float, 1><<<blocks, kEbThreads, 0, s>>>(a);
-            else k_epilogue_bwd<__nv_bfloat16, 1><<<blocks, kEbThreads, 0, s>>>(a);
+            if (dtype == DFW_F32) DFW_EB_GO(float, 1);
+            else DFW_EB_GO(__nv_bfloat16, 1);
         } else {
-            if (dtype == DFW_F32) k_epilogue_bwd<float, 2><<<blocks, kEbThreads, 0, s>>>(a);
-            else k_epilogue_bwd<__nv_bfloat16, 2><<<blocks, kEbThreads, 0, s>>>(a);
+            if (dtype == DFW_F32) DFW_EB_GO(float, 2);
+            else DFW_EB_GO(__nv_bfloat16, 2);
         }
+#undef DFW_EB_GO
         DFW_LAUNCH_CHECK();
     }
     if (need_cols) {
