@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float a = act ? y[r][v][j] : 1.f;
-                        if (has_rowdot) c0[v][j] += gr[r] * (a * keep[j]);  // d_rowdot_w (a is post-ReLU)
+                        if (has_rowdot) c0[v][j] += gr[r] * a;  // d_rowdot_w: `act` is the saved output, i.e. already post-ReLU AND post-dropout
                         float gg = g[r][v][j] * keep[j];
                         if (relu && !(a > 0.f)) gg = 0.f;
                         g[r][v][j] = gg;

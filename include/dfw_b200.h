@@ -139,7 +139,7 @@ int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1,
 /* ------------------------------------------------------------------------------------------
  * (d1) backward of the epilogue of (c): given g_out = dL/d out, produce g_y = dL/d y.
  *      Recomputes xhat/relu mask from pre_out + ln_stats and the dropout mask from seed.
- *      Without DFW_EP_LAYERNORM, `act` (the saved post-ReLU output) gives the ReLU mask.
+ *      Without DFW_EP_LAYERNORM, `act` (the saved forward OUTPUT: post-ReLU and post-dropout) gives the ReLU mask and the row-dot operand.
  *      dgamma/dbeta fp32 [Hout] (LayerNorm only).  ws: dfw_epilogue_bwd_ws_bytes.
  *      rowdot variant: g_rowdot fp32 [N] (dL/d rowdot_out) replaces g_out, and
  *      d_rowdot_w [Hout], d_rowdot_b [1] are produced.  d_bias (nullable, fp32 [Hout]) receives the column sums

@@ -159,6 +159,47 @@ class GraphSAGEModelRef(nn.Module):
             return self.forward(data.x, data.edge_index, getattr(data, "batch", None))
 
 
+# --------------------------------------------------------------------------------------
+# Train-mode parity: the reference draws dropout masks from torch's RNG (model.py:70,93), which no other
+# implementation can reproduce, so train-mode tests run the oracle with the PRODUCT's masks.  This is a numpy
+# restatement of the product's counter RNG (deep-fem-uav-wing_b200/csrc/dfw_common.cuh: mix32 / dropout_row_key /
+# dropout_bits) - test infrastructure like the rest of this module.
+# --------------------------------------------------------------------------------------
+def _mix32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x = (x.astype(np.uint64) * np.uint64(0x21F0AAAD) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    x ^= x >> np.uint32(15)
+    x = (x.astype(np.uint64) * np.uint64(0x735A2D97) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    x ^= x >> np.uint32(15)
+    return x
+
+
+def dropout_keep_scale(seed: int, n_rows: int, n_cols: int, p: float) -> np.ndarray:
+    """[n_rows, n_cols] float32: 1/(1-p) where the product keeps the unit, 0 where it drops it."""
+    seed &= 0xFFFFFFFFFFFFFFFF
+    rows = np.arange(n_rows, dtype=np.uint64)
+    k = _mix32(((rows & np.uint64(0xFFFFFFFF)) ^ np.uint64(seed & 0xFFFFFFFF)).astype(np.uint32))
+    k = ((k.astype(np.uint64) + (rows >> np.uint64(32)) * np.uint64(0x85EBCA6B) + np.uint64(seed >> 32)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    k = _mix32(k)
+    cols = (np.arange(n_cols, dtype=np.uint64) * np.uint64(0x9E3779B9)) & np.uint64(0xFFFFFFFF)
+    bits = _mix32(((k.astype(np.uint64)[:, None] + cols[None, :]) & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+    thr = min(max(int(float(np.float32(p)) * 4294967296.0), 0), 4294967295)  # dropout_threshold()
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return np.where(bits >= np.uint32(thr), scale, np.float32(0.0)).astype(np.float32)
+
+
+def forward_with_masks(model: "GraphSAGEModelRef", x, edge_index, layer_masks, decoder_mask):
+    """``GraphSAGEModelRef.forward`` in training mode with the dropout factors given (model.py:86-98)."""
+    h = model.encoder(x)
+    for conv, norm, m in zip(model.convs, model.norms, layer_masks):
+        h_new = F.relu(norm(conv(h, edge_index)))
+        h = h + h_new * m
+    dec = model.decoder
+    hid = F.relu(dec[0](h)) * decoder_mask
+    return dec[3](hid)
+
+
 class MaskedMSELossRef(nn.Module):
     """Restates ``MaskedMSELoss`` (``model.py:115-153``)."""
 

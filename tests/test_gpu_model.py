@@ -330,3 +330,41 @@ def test_build_graph_data_device_matches_reference_fixture():
     assert np.array_equal(dev["x"].cpu().numpy(), host["x"])
     assert np.all(np.abs(dev["y"].cpu().numpy() - host["y"]) <= 2 * np.spacing(np.abs(host["y"])))
     assert np.array_equal(dev["edge_index"].cpu().numpy(), canon_edges(host["edge_index"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,layers,p", [(64, 2, 0.1), (128, 4, 0.3)])
+def test_train_mode_matches_oracle_with_the_same_dropout_masks(h, layers, p):
+    """Training mode, dropout on: forward, loss and every gradient against the oracle evaluated with the masks the
+    kernels draw (restated from the counter RNG in oracle/sage_oracle.py).  Covers the dropout branch of the fused
+    epilogue, its regeneration in the LayerNorm-tail backward and the decoder tail."""
+    from deep_fem_uav_wing.gnn import model as gm
+    from deep_fem_uav_wing.gnn import synth
+    from oracle.sage_oracle import dropout_keep_scale, forward_with_masks
+
+    GraphSAGEModel, MaskedMSELoss, _, _ = _models()
+    mesh = synth.surface_tri_wing(6000, seed=3)
+    n = mesh["num_nodes"]
+    x, ei = torch.from_numpy(mesh["x"]), torch.from_numpy(mesh["edge_index"])
+    y, m = torch.from_numpy(mesh["y"]), torch.from_numpy(mesh["loss_mask"])
+    torch.manual_seed(11)
+    ref = GraphSAGEModelRef(10, h, 1, layers, dropout=p).train()
+    model = GraphSAGEModel(10, h, 1, layers, dropout=p)
+    model.load_state_dict(ref.state_dict(), strict=True)
+    model = model.cuda().train()
+    torch.manual_seed(77)
+    seed = int(torch.randint(0, 2**62, (1,)).item())  # what model.forward will draw (gnn/model.py:_next_seed)
+    torch.manual_seed(77)
+    out = model(x.cuda(), ei.cuda())
+    loss = MaskedMSELoss()(out, y.cuda(), m.cuda())
+    loss.backward()
+    layer_masks = [torch.from_numpy(dropout_keep_scale(seed + 0x632BE5AB * (i + 1), n, h, p)) for i in range(layers)]
+    dec_mask = torch.from_numpy(dropout_keep_scale(seed + 0x7F4A7C15, n, 64, p))
+    assert abs(float((layer_masks[0] > 0).float().mean()) - (1 - p)) < 0.01
+    out_ref = forward_with_masks(ref, x, ei, layer_masks, dec_mask)
+    loss_ref = MaskedMSELossRef()(out_ref, y, m)
+    loss_ref.backward()
+    assert rel_max(out.cpu(), out_ref.detach()) < TOL_FP32
+    assert abs(loss.item() - loss_ref.item()) <= TOL_FP32 * abs(loss_ref.item())
+    for (k, q), qr in zip(model.named_parameters(), ref.parameters()):
+        assert rel_l2(q.grad.cpu(), qr.grad) < TOL_FP32, (k, rel_l2(q.grad.cpu(), qr.grad))
