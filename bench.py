@@ -305,6 +305,17 @@ def main():
     clocks = sampler.stop()
     value = BATCH * steps * world / (ms_total * 1e-3)
 
+    # ---- inference arm (BASELINE metric: "train/infer"): eval-mode forward over the same resident batches ----
+    model.eval()
+    with torch.no_grad():
+        for i in range(3):
+            model(resident[i % n_batches].x, resident[i % n_batches].edge_index)
+        ms_inf = timed_region(lambda i: model(resident[(warmup + i) % n_batches].x, resident[(warmup + i) % n_batches].edge_index), steps,
+                              dist_on, device)
+    model.train()
+    infer = {"value": BATCH * steps * world / (ms_inf * 1e-3), "unit": "meshes/s", "ms_per_step": ms_inf / steps,
+             "nodes_per_sec": BATCH * steps * world * NODES / (ms_inf * 1e-3), "what": "eval-mode forward, device-resident batches, CSR cached"}
+
     # ---- roofline pass: same steps with per-launch CUDA events ---------------------------------
     prof_steps = min(steps, 8)
     ops.PROFILER = ops.KernelProfiler()
@@ -414,6 +425,10 @@ def main():
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world),
             "nodes_per_sec": value * NODES, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "infer": infer,
+            "aggregation": {"kernel": "dfw_sage_aggregate (forward mean, this workload)", "achieved_GBps": kernels.get("aggregate", {}).get("achieved_GBps"),
+                            "hbm_frac": kernels.get("aggregate", {}).get("hbm_frac"),
+                            "config4": "2M nodes / 27M edges / H=256 bf16: profiles/r01_cfg4_2M_bf16.jsonl (tools/bench_configs.py cfg4)"},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         }
         emit(line)

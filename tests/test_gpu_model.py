@@ -335,7 +335,12 @@ def test_build_graph_data_device_matches_reference_fixture():
 @pytest.mark.gpu
 @pytest.mark.parametrize("h,layers,p,dtype,out_ch", [(64, 2, 0.1, torch.float32, 1), (128, 4, 0.3, torch.float32, 1),
                                                      (128, 3, 0.2, torch.bfloat16, 1), (256, 2, 0.1, torch.float32, 1),
-                                                     (64, 2, 0.25, torch.float32, 3)])
+                                                     (64, 2, 0.25, torch.float32, 3),
+                                                     # widths the tensor-core path cannot take (SIMT linears, split-K dW,
+                                                     # sub-warp aggregation, ragged LayerNorm lanes)
+                                                     (4, 2, 0.2, torch.float32, 1), (20, 2, 0.2, torch.float32, 1),
+                                                     (36, 1, 0.1, torch.float32, 2), (96, 2, 0.1, torch.float32, 1),
+                                                     (40, 2, 0.1, torch.bfloat16, 1)])
 def test_train_mode_matches_oracle_with_the_same_dropout_masks(h, layers, p, dtype, out_ch):
     """Training mode, dropout on: forward, loss and every gradient against the oracle evaluated with the masks the
     kernels draw (restated from the counter RNG in oracle/sage_oracle.py).  Covers the dropout branch of the fused
