@@ -388,3 +388,49 @@ def test_train_mode_matches_oracle_with_the_same_dropout_masks(h, layers, p, dty
     for (k, q), qr, q64 in zip(model.named_parameters(), ref.parameters(), ref64.parameters()):
         e_kernel, e_oracle = rel_l2(q.grad.cpu(), q64.grad), rel_l2(qr.grad, q64.grad)
         assert e_kernel < max(tol, 3 * e_oracle), (k, e_kernel, e_oracle)
+
+
+@pytest.mark.gpu
+def test_degenerate_graphs_match_oracle_forward_and_backward():
+    """SURVEY 8c's known-answer shapes through the whole model: no edges at all, a single node, isolated nodes
+    (mean over nothing = 0), self loops, duplicate edges (counted with multiplicity), a one-directional edge, one very
+    high-degree hub, and node counts around the 128-row tile boundary."""
+    GraphSAGEModel, MaskedMSELoss, _, _ = _models()
+    rng = np.random.default_rng(5)
+
+    def hub(n):  # every node points at node 0, plus a few random edges
+        src = np.concatenate([np.arange(1, n), rng.integers(0, n, 50)])
+        dst = np.concatenate([np.zeros(n - 1, dtype=np.int64), rng.integers(0, n, 50)])
+        return np.stack([src, dst]).astype(np.int64)
+
+    cases = {
+        "no_edges": (300, np.zeros((2, 0), dtype=np.int64)),
+        "single_node": (1, np.zeros((2, 0), dtype=np.int64)),
+        "single_node_self_loop": (1, np.array([[0, 0], [0, 0]], dtype=np.int64)),
+        "path_isolated_selfloop_duplicate": (6, np.array([[0, 1, 1, 2, 2, 2, 4, 4], [1, 0, 2, 1, 1, 2, 4, 3]], dtype=np.int64)),
+        "one_directional": (4, np.array([[0], [3]], dtype=np.int64)),
+        "hub_127": (127, hub(127)), "hub_128": (128, hub(128)), "hub_129": (129, hub(129)), "hub_5000": (5000, hub(5000)),
+    }
+    for name, (n, ei_np) in cases.items():
+        torch.manual_seed(3)
+        ref = GraphSAGEModelRef(10, 64, 1, 2, dropout=0.0)
+        model = GraphSAGEModel(10, 64, 1, 2, dropout=0.0)
+        model.load_state_dict(ref.state_dict())
+        model = model.cuda()
+        x = torch.from_numpy(rng.standard_normal((n, 10)).astype(np.float32))
+        y = torch.from_numpy(rng.standard_normal((n, 1)).astype(np.float32))
+        m = torch.from_numpy(rng.random(n) > 0.2)
+        if not m.any():
+            m[0] = True
+        ei = torch.from_numpy(ei_np)
+        out_ref = ref(x, ei)
+        MaskedMSELossRef()(out_ref, y, m).backward()
+        out = model(x.cuda(), ei.cuda())
+        MaskedMSELoss()(out, y.cuda(), m.cuda()).backward()
+        assert out.shape == (n, 1), name
+        assert rel_max(out.cpu(), out_ref.detach()) < TOL_FP32, name
+        for (k, q), qr in zip(model.named_parameters(), ref.parameters()):
+            if qr.grad.norm() == 0:
+                assert q.grad.abs().max().item() < 1e-12, (name, k)
+            else:
+                assert rel_l2(q.grad.cpu(), qr.grad) < 2 * TOL_FP32, (name, k, rel_l2(q.grad.cpu(), qr.grad))
