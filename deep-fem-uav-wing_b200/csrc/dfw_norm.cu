@@ -233,6 +233,103 @@ __global__ void __launch_bounds__(kEbThreads, VPL == 1 ? 2 : 1) k_epilogue_bwd(c
     }
 }
 
+// Backward of the LayerNorm-free epilogues (encoder linears: ReLU; decoder tail: ReLU + dropout + row-dot), i.e. the
+// calls with no row statistics.  Purely element-wise plus column sums, so rows are PACKED: H/4 threads per row and
+// 256/(H/4) rows per block step (the generic kernel above gives a row a whole warp and leaves half of its lanes idle
+// at H = 64).  A thread's column group is fixed, so its column partials stay in registers; the row groups of a block
+// are added in a fixed order.  Same `part` layout and second pass as the generic kernel.
+template <typename T>
+__global__ void __launch_bounds__(kEbThreads) k_act_bwd(const EbArgs p) {
+    extern __shared__ float s_cols[];  // [3][rows_per_step][H]
+    __shared__ float s_gr[kEbThreads];
+    const int H = p.H, tpr = H / 4, rps = kEbThreads / tpr;
+    const int rl = threadIdx.x / tpr, cl = (threadIdx.x % tpr) * 4;
+    const bool active = rl < rps;
+    const bool relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT, has_rowdot = p.g_rowdot != nullptr;
+    const uint64_t seed_v = drop ? resolve_seed(p.seed, p.flags) : 0ull;
+    const T* gout = (const T*)p.g_out;
+    const T* act = (const T*)p.act;
+    T* gy = (T*)p.g_y;
+    float rdw[4] = {0.f, 0.f, 0.f, 0.f};
+    if (has_rowdot && active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rdw[j] = __ldg(p.rowdot_w + cl + j);
+    }
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+    float sum_gr = 0.f;
+    constexpr int kR = 4;  // rows in flight per thread
+    const int64_t step = (int64_t)gridDim.x * rps;
+    if (active) {
+        for (int64_t row0 = (int64_t)blockIdx.x * rps + rl; row0 < p.N; row0 += step * kR) {
+            float g[kR][4], y[kR][4], gr[kR];
+            bool rv[kR];
+#pragma unroll
+            for (int r = 0; r < kR; ++r) {
+                const int64_t row = row0 + r * step;
+                rv[r] = row < p.N;
+                gr[r] = 0.f;
+                if (rv[r]) {
+                    const int64_t off = row * H + cl;
+                    if (has_rowdot) gr[r] = __ldg(p.g_rowdot + row);
+                    else ld4(gout + off, g[r]);
+                    if (act) ld4(act + off, y[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kR; ++r) {
+                if (!rv[r]) continue;
+                const int64_t row = row0 + r * step;
+                if (has_rowdot && cl == 0) sum_gr += gr[r];
+                float keep[4] = {1.f, 1.f, 1.f, 1.f};
+                if (drop) {
+                    const uint32_t row_key = dropout_row_key(seed_v, (uint64_t)row);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) keep[j] = dropout_bits(row_key, (uint32_t)(cl + j)) >= p.drop_thr ? p.drop_scale : 0.f;
+                }
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = act ? y[r][j] : 1.f;
+                    float gg = has_rowdot ? gr[r] * rdw[j] : g[r][j];
+                    if (has_rowdot) c0[j] += gr[r] * a;  // d_rowdot_w: `act` is the saved output (post-ReLU, post-dropout)
+                    gg *= keep[j];
+                    if (relu && !(a > 0.f)) gg = 0.f;
+                    o[j] = gg;
+                    c2[j] += gg;
+                }
+                st4(gy + row * H + cl, o);
+            }
+        }
+    }
+    if (!p.part) return;
+    float* sc0 = s_cols;
+    float* sc2 = s_cols + (size_t)rps * H;
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sc0[rl * H + cl + j] = c0[j];
+            sc2[rl * H + cl + j] = c2[j];
+        }
+    }
+    s_gr[threadIdx.x] = (active && cl == 0) ? sum_gr : 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += kEbThreads) {
+        float a = 0.f, d = 0.f;
+        for (int q = 0; q < rps; ++q) {
+            a += sc0[q * H + c];
+            d += sc2[q * H + c];
+        }
+        p.part[((int64_t)blockIdx.x * 4 + 0) * H + c] = a;
+        p.part[((int64_t)blockIdx.x * 4 + 1) * H + c] = 0.f;
+        p.part[((int64_t)blockIdx.x * 4 + 3) * H + c] = d;
+    }
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int q = 0; q < kEbThreads; ++q) t += s_gr[q];
+        p.part[((int64_t)blockIdx.x * 4 + 2) * H] = t;
+    }
+}
+
 // Second pass of the column reductions: one WARP per (slot, column); lanes stride over the per-block partials and
 // a fixed shuffle tree combines them (deterministic).  A thread-per-column loop over ~600 partials is a chain of
 // ~600 dependent L2 loads and took longer than the main kernel.
@@ -369,6 +466,13 @@ extern "C" int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const 
     a.g_y = g_y; a.part = need_cols ? reinterpret_cast<float*>(ws) : nullptr;
     a.N = N; a.H = (int)Hout; a.flags = flags;
     if (N > 0) {
+        if (!ln) {  // no row statistics: packed-row element-wise kernel
+            const int tpr = (int)Hout / 4, rps = kEbThreads / tpr;
+            const size_t smem = sizeof(float) * 2 * (size_t)rps * (size_t)Hout;
+            if (dtype == DFW_F32) k_act_bwd<float><<<blocks, kEbThreads, smem, s>>>(a);
+            else k_act_bwd<__nv_bfloat16><<<blocks, kEbThreads, smem, s>>>(a);
+            DFW_LAUNCH_CHECK();
+        } else {
         // the SAGE layer's tail gets the specialised instantiation
         const bool tail = ln && (flags & DFW_EP_RELU) && g_out && !g_rowdot;
         const int spec = tail ? ((flags & DFW_EP_DROPOUT) ? 3 : 1) : 0;
@@ -387,6 +491,7 @@ extern "C" int dfw_epilogue_bwd(const void* g_out, const float* g_rowdot, const 
         }
 #undef DFW_EB_GO
         DFW_LAUNCH_CHECK();
+        }
     }
     if (need_cols) {
         float* o0 = ln ? dgamma : d_rowdot_w;
