@@ -13,7 +13,7 @@ _PKG_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 LIB_PATH = os.environ.get("DFW_B200_LIB", os.path.join(_PKG_ROOT, "lib", "libdfw_b200.so"))
 
 DFW_F32, DFW_BF16 = 0, 1
-EP_RELU, EP_LAYERNORM, EP_RESIDUAL, EP_DROPOUT, EP_SEED_IS_PTR = 1, 2, 4, 8, 16
+EP_RELU, EP_LAYERNORM, EP_RESIDUAL, EP_DROPOUT, EP_SEED_IS_PTR, EP_TRANSPOSE_W = 1, 2, 4, 8, 16, 32
 
 # name -> (restype, argtypes); must list every symbol of include/dfw_b200.h
 SIGNATURES = {
@@ -36,6 +36,7 @@ SIGNATURES = {
                                c_float, c_void_p, c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "dfw_linear_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "dfw_linear_tc_eligible": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "dfw_epilogue_bwd_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "dfw_epilogue_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,

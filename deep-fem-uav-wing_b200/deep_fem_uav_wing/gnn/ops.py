@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 import torch
 
 from . import _cabi
-from ._cabi import DFW_BF16, DFW_F32, EP_DROPOUT, EP_LAYERNORM, EP_RELU, EP_RESIDUAL, EP_SEED_IS_PTR, check, lib
+from ._cabi import DFW_BF16, DFW_F32, EP_DROPOUT, EP_LAYERNORM, EP_RELU, EP_RESIDUAL, EP_SEED_IS_PTR, EP_TRANSPOSE_W, check, lib
 
 _DTYPES = {torch.float32: DFW_F32, torch.bfloat16: DFW_BF16}
 LAUNCH_COUNTER = {"kernels": 0}  # kernels launched through the C ABI (bench.py's gpu_launches)
@@ -316,13 +316,24 @@ def aggregate_scaled(rowptr, col, src_scale, x, label="aggregate_bwd"):
 
 
 def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=False, residual=None, dropout_p=0.0, seed=0,
-               save_pre=False, rowdot=None, want_out=True, label="linear_fwd"):
-    """See ``dfw_linear_fwd``.  ``ln`` = (gamma, beta); ``rowdot`` = (w fp32 [Hout], b fp32 [1] or None)."""
+               save_pre=False, rowdot=None, want_out=True, transpose_w=False, label="linear_fwd"):
+    """See ``dfw_linear_fwd``.  ``ln`` = (gamma, beta); ``rowdot`` = (w fp32 [Hout], b fp32 [1] or None).
+    ``transpose_w``: ``w1``/``w2`` are ``[k, Hout]`` (a forward layer's weights used by its input gradient)."""
     _require_cuda(a1, "input")
     N, k1 = a1.shape
-    Hout = w1.shape[0]
     dev, dt = a1.device, a1.dtype
     flags = 0
+    if transpose_w:
+        Hout = w1.shape[1]
+        k2_ = 0 if a2 is None else a2.shape[1]
+        ptrs_ok = all(t is None or t.data_ptr() % 16 == 0 for t in (a1, a2, residual))
+        if ptrs_ok and lib.dfw_linear_tc_eligible(N, Hout, k1, k2_, _dt(a1)):
+            flags |= EP_TRANSPOSE_W  # the transposition rides in the weight-preparation launch
+        else:
+            w1 = w1.t().contiguous()
+            w2 = w2.t().contiguous() if w2 is not None else None
+    else:
+        Hout = w1.shape[0]
     if relu:
         flags |= EP_RELU
     if ln is not None:
@@ -531,8 +542,8 @@ class SageConvFn(torch.autograd.Function):
             # (8 -> 6 passes over [N, H] tensors).
             rp_t, col_t = graph.transpose()
             g_t = aggregate_scaled(rp_t, col_t, graph.inv_deg, g_y)
-            g_x, _, _, _ = linear_fwd(g_t, wl.t().contiguous(), g_y, wr.t().contiguous(),
-                                      residual=g_out if ctx.fused_tail else None, label="linear_bwd_input")
+            g_x, _, _, _ = linear_fwd(g_t, wl, g_y, wr, residual=g_out if ctx.fused_tail else None, transpose_w=True,
+                                      label="linear_bwd_input")
         return g_x, dwl, dbl, dwr, dgamma, dbeta, None, None, None, None, None
 
 

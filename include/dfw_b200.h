@@ -40,8 +40,11 @@ enum {
     DFW_EP_LAYERNORM = 2, /* row LayerNorm(eps, gamma, beta) before ReLU        model.py:64,91          */
     DFW_EP_RESIDUAL = 4,  /* out = residual + epilogue(...)                     model.py:95             */
     DFW_EP_DROPOUT = 8,   /* inverted dropout (train only)                      model.py:93, :70        */
-    DFW_EP_SEED_IS_PTR = 16 /* `seed` is a DEVICE pointer to one uint64 (read by the kernel): lets a captured CUDA graph
+    DFW_EP_SEED_IS_PTR = 16, /* `seed` is a DEVICE pointer to one uint64 (read by the kernel): lets a captured CUDA graph
                              draw a fresh dropout mask on every replay */
+    DFW_EP_TRANSPOSE_W = 32 /* dfw_linear_fwd only: w1/w2 are given as [k, Hout] row-major (the FORWARD layer's weights,
+                             used by its input gradient g W instead of x W^T); the transposition rides in the weight
+                             preparation launch.  Needs a tensor-core eligible shape: ask dfw_linear_tc_eligible */
 };
 
 const char* dfw_last_error(void);
@@ -127,6 +130,9 @@ int dfw_sage_aggregate_scaled(const int32_t* rowptr, const int32_t* col, const f
  *     16 <= Hout <= 256, Hout % 16 == 0, k*sizeof(dtype) % 16 == 0 and `ws` holds dfw_linear_ws_bytes();
  *     other shapes (e.g. the encoder's K = 10) run the exact-fp32 SIMT kernel.  ws may be NULL (SIMT). */
 size_t dfw_linear_ws_bytes(int64_t Hout, int64_t k1, int64_t k2, int dtype);
+/*     1 when (N, Hout, k1, k2, dtype) takes the tensor-core path given 16-byte aligned operands and a workspace
+ *     (needed before asking for DFW_EP_TRANSPOSE_W); no CUDA call. */
+int dfw_linear_tc_eligible(int64_t N, int64_t Hout, int64_t k1, int64_t k2, int dtype);
 int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1,
                    const void* a2, const void* w2, int64_t k2,
                    const float* bias, const float* ln_gamma, const float* ln_beta, float ln_eps,

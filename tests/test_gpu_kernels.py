@@ -203,6 +203,28 @@ def test_linear_fwd_and_bwd_pieces(ops, hout, k1, k2, dtype):
     assert torch.equal(dw1, dw1b)  # fixed-order split reduction: bit-reproducible
 
 
+@pytest.mark.parametrize("kin,hout", [(128, 128), (64, 128), (256, 64), (24, 40)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_transposed_weights_equal_pretransposed(ops, kin, hout, dtype):
+    """DFW_EP_TRANSPOSE_W (the SAGE layer's input gradient ``g_t W_l + g_y W_r + g_out`` on the forward's weights) is
+    bit-identical to handing over ``W.t().contiguous()``; (24, 40) is not tensor-core eligible and takes the wrapper's
+    explicit transposition."""
+    torch.manual_seed(kin * 3 + hout)
+    n, dev = 1501, "cuda"
+    g_t = torch.randn(n, hout, device=dev).to(dtype)
+    g_y = torch.randn(n, hout, device=dev).to(dtype)
+    wl = (torch.randn(hout, kin, device=dev) / hout**0.5).to(dtype)  # forward layout [Hout, K]
+    wr = (torch.randn(hout, kin, device=dev) / hout**0.5).to(dtype)
+    g_out = torch.randn(n, kin, device=dev).to(dtype)
+    a, _, _, _ = ops.linear_fwd(g_t, wl, g_y, wr, residual=g_out, transpose_w=True)
+    b, _, _, _ = ops.linear_fwd(g_t, wl.t().contiguous(), g_y, wr.t().contiguous(), residual=g_out)
+    assert a.shape == (n, kin) and torch.equal(a, b)
+    ref = g_t.double() @ wl.double() + g_y.double() @ wr.double() + g_out.double()
+    assert rel_max(a.double(), ref) < (TOL_FP32 if dtype == torch.float32 else TOL_BF16)
+    c, _, _, _ = ops.linear_fwd(g_t, wl, transpose_w=True)
+    assert rel_max(c.double(), g_t.double() @ wl.double()) < (TOL_FP32 if dtype == torch.float32 else TOL_BF16)
+
+
 def test_masked_mse_matches_reference_fixture(ops):
     from helpers import load_golden
 
