@@ -287,8 +287,6 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         const bool rok = row < p.N;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const int H = p.Hout;
-        if (TF32) tmem_combine(t_row, H, p.nacc + 1, p.Npad);
-        if (et == 0) PROBE(42);  // hi/cross accumulators combined
         const int n32 = H / 32;
         const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
         const bool ln = p.flags & DFW_EP_LAYERNORM;
@@ -302,9 +300,8 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         int n_store = 0;  // TMA stores issued so far (staging buffer = n_store % nbuf)
         float mean = 0.f, rstd = 1.f;
 
-        // y = (acc + bias) * row_scale for 32 columns starting at c0
-        auto load_y = [&](int c0, float* v) {
-            tmem_ld32(t_row + c0, v);
+        // y = (acc + bias) * row_scale for the 32 columns starting at c0
+        auto finish_y = [&](int c0, float* v) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const float4 b = bias4[c0 / 4 + g];
@@ -350,31 +347,68 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             }
             ++n_store;
         };
+        // Every pass walks the row 32 columns at a time with the TMEM load of the NEXT group in flight while the
+        // current one is worked on (the values are copied out of the load's registers first, so one register set per
+        // region is enough).
 
-        // ---- pass 1: row sum (LayerNorm mean) and the pre-activation tensor y ----
-        if (ln || p.pre_out) {
+        // ---- pass 1: sum the accumulator regions (3xTF32: hi*hi [+ hi*hi] + cross, round-to-nearest), y = (acc + bias) *
+        // row_scale written BACK to region 0 (passes 2 and 3 read finished values), row sum for LayerNorm, and the
+        // pre-activation tensor ----
+        const int regions = TF32 ? p.nacc + 1 : 1;
+        const bool y_in_tmem = TF32 || ln || p.pre_out;
+        if (y_in_tmem) {
             float s = 0.f;
-            for (int ob = 0; ob < out_boxes; ++ob) {
-                uint8_t* box = p.pre_out ? acquire_box() : nullptr;
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(t_row, ra);
+            if (regions > 1) tmem_ld32_issue(t_row + p.Npad, rb);
+            uint8_t* box = nullptr;
+            for (int g = 0; g < n32; ++g) {
+                const int c0 = g * 32;
+                if (p.pre_out && c0 % EPC == 0) box = acquire_box();
+                float v[32];
+                tmem_ld_wait(ra);
+                if (regions > 1) {
+                    tmem_ld_wait(rb);
 #pragma unroll
-                for (int h = 0; h < EPC / 32; ++h) {
-                    float v[32];
-                    load_y(ob * EPC + h * 32, v);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+                    if (regions > 2) {
+                        float w[32];
+                        tmem_ld32(t_row + 2 * p.Npad + c0, w);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) s += v[j];
-                    if (p.pre_out) stage_row(box, h * 32, v);
+                        for (int j = 0; j < 32; ++j) v[j] += w[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
                 }
-                if (p.pre_out) release_box(&maps.pre, box, ob * EPC);
+                if (g + 1 < n32) {
+                    tmem_ld32_issue(t_row + c0 + 32, ra);
+                    if (regions > 1) tmem_ld32_issue(t_row + p.Npad + c0 + 32, rb);
+                }
+                finish_y(c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s += v[j];
+                tmem_st32_nowait(t_row + c0, v);
+                if (p.pre_out) {
+                    stage_row(box, c0 % EPC, v);
+                    if ((c0 + 32) % EPC == 0) release_box(&maps.pre, box, c0 / EPC * EPC);
+                }
             }
+            tmem_st_wait();
             mean = s / (float)H;
         }
-        if (et == 0) PROBE(43);  // pass 1 (pre-activation staged + stored)
+        if (et == 0) PROBE(43);  // pass 1 (accumulators combined, pre-activation staged + stored)
         // ---- pass 2: variance around the mean (two-pass, like torch) ----
         if (ln) {
             float qs = 0.f;
-            for (int cc = 0; cc < n32; ++cc) {
+            uint32_t ra[32];
+            tmem_ld32_issue(t_row, ra);
+            for (int g = 0; g < n32; ++g) {
                 float v[32];
-                load_y(cc * 32, v);
+                tmem_ld_wait(ra);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+                if (g + 1 < n32) tmem_ld32_issue(t_row + (g + 1) * 32, ra);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float d = v[j] - mean;
@@ -392,22 +426,29 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         if (p.residual) mbar_wait(res_full, 0);
         if (et == 0) PROBE(45);  // residual tile in smem
         float dot = 0.f;
-        for (int ob = 0; ob < out_boxes; ++ob) {
-            uint8_t* box = p.out ? acquire_box() : nullptr;
-            const uint8_t* rbox = smem + L.res + (size_t)ob * kTileM * kChunkBytes;
-#pragma unroll
-            for (int h = 0; h < EPC / 32; ++h) {
-                const int c0 = ob * EPC + h * 32;
+        {
+            uint32_t ra[32];
+            tmem_ld32_issue(t_row, ra);
+            uint8_t* box = nullptr;
+            for (int g = 0; g < n32; ++g) {
+                const int c0 = g * 32;
+                const int ob = c0 / EPC, h = (c0 % EPC) / 32;
+                if (p.out && c0 % EPC == 0) box = acquire_box();
+                const uint8_t* rbox = smem + L.res + (size_t)ob * kTileM * kChunkBytes;
                 float v[32];
-                load_y(c0, v);
+                tmem_ld_wait(ra);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+                if (g + 1 < n32) tmem_ld32_issue(t_row + c0 + 32, ra);
+                if (!y_in_tmem) finish_y(c0, v);
                 if (ln) {
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float4 ga = gam4[c0 / 4 + g], be = bet4[c0 / 4 + g];
-                        v[4 * g] = (v[4 * g] - mean) * rstd * ga.x + be.x;
-                        v[4 * g + 1] = (v[4 * g + 1] - mean) * rstd * ga.y + be.y;
-                        v[4 * g + 2] = (v[4 * g + 2] - mean) * rstd * ga.z + be.z;
-                        v[4 * g + 3] = (v[4 * g + 3] - mean) * rstd * ga.w + be.w;
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 ga = gam4[c0 / 4 + g4], be = bet4[c0 / 4 + g4];
+                        v[4 * g4] = (v[4 * g4] - mean) * rstd * ga.x + be.x;
+                        v[4 * g4 + 1] = (v[4 * g4 + 1] - mean) * rstd * ga.y + be.y;
+                        v[4 * g4 + 2] = (v[4 * g4 + 2] - mean) * rstd * ga.z + be.z;
+                        v[4 * g4 + 3] = (v[4 * g4 + 3] - mean) * rstd * ga.w + be.w;
                     }
                 }
                 if (relu) {
@@ -423,36 +464,38 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 }
                 if (p.rowdot_out) {
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float4 w = rdw4[c0 / 4 + g];
-                        dot = fmaf(v[4 * g], w.x, dot);
-                        dot = fmaf(v[4 * g + 1], w.y, dot);
-                        dot = fmaf(v[4 * g + 2], w.z, dot);
-                        dot = fmaf(v[4 * g + 3], w.w, dot);
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 w = rdw4[c0 / 4 + g4];
+                        dot = fmaf(v[4 * g4], w.x, dot);
+                        dot = fmaf(v[4 * g4 + 1], w.y, dot);
+                        dot = fmaf(v[4 * g4 + 2], w.z, dot);
+                        dot = fmaf(v[4 * g4 + 3], w.w, dot);
                     }
                 }
                 if (p.residual) {
                     if constexpr (sizeof(T) == 4) {
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(rbox + box_off(r_in_tile, h * 8 + g));
-                            v[4 * g] += r4.x; v[4 * g + 1] += r4.y; v[4 * g + 2] += r4.z; v[4 * g + 3] += r4.w;
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rbox + box_off(r_in_tile, h * 8 + g4));
+                            v[4 * g4] += r4.x; v[4 * g4 + 1] += r4.y; v[4 * g4 + 2] += r4.z; v[4 * g4 + 3] += r4.w;
                         }
                     } else {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g4 = 0; g4 < 4; ++g4) {
                             Vec16<T> u;
-                            u.v = *reinterpret_cast<const uint4*>(rbox + box_off(r_in_tile, h * 4 + g));
+                            u.v = *reinterpret_cast<const uint4*>(rbox + box_off(r_in_tile, h * 4 + g4));
                             float f[8];
                             u.to_float(f);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[8 * g + i] += f[i];
+                            for (int i = 0; i < 8; ++i) v[8 * g4 + i] += f[i];
                         }
                     }
                 }
-                if (p.out) stage_row(box, h * 32, v);
+                if (p.out) {
+                    stage_row(box, h * 32, v);
+                    if ((c0 + 32) % EPC == 0) release_box(&maps.out, box, ob * EPC);
+                }
             }
-            if (p.out) release_box(&maps.out, box, ob * EPC);
         }
         if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
         if (et == 0) PROBE(46);  // pass 3 done
