@@ -76,7 +76,7 @@ __host__ __device__ inline Smem carve(bool tf32, int Npad, int stages, int out_b
 }
 
 #ifdef DFW_TC_PROBE
-__device__ long long* g_probe = nullptr;  // [64] stamps of one mid-grid CTA (tools/tc_timeline.py)
+__device__ long long* g_probe = nullptr;  // [96] stamps of one mid-grid CTA (tools/tc_timeline.py)
 __device__ __forceinline__ void probe(int slot) {
     if (g_probe && blockIdx.x == gridDim.x / 2) {
         long long t;
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     uint64_t* res_full = accum_full + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
 
+    if (threadIdx.x == 0) PROBE(65);  // kernel entry
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m_base = (int64_t)blockIdx.x * kTileM;  // CTAs padding the grid to whole clusters own an empty tile
     const int total_chunks = p.chunks[0] + p.chunks[1];
@@ -125,18 +126,24 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     const uint32_t csize = cluster_nctarank(), crank = csize > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&maps.a[0]);
-        prefetch_tmap(&maps.w_hi[0]);
-        if (p.chunks[1]) {
-            prefetch_tmap(&maps.a[1]);
-            prefetch_tmap(&maps.w_hi[1]);
+    // One chunk = one pipeline stage: the activation box of this CTA's rows plus the weight boxes of the same K range.
+    const uint32_t stage_tx = (uint32_t)(kTileM * CB + p.Npad * CB * (TF32 ? 2 : 1));
+    auto issue_chunk = [&](int c, int stage) {
+        const int seg = c >= p.chunks[0];
+        const int kc = (seg ? c - p.chunks[0] : c) * KPC;
+        uint8_t* st = smem + (size_t)stage * L.stage_bytes;
+        mbar_arrive_expect_tx(&full[stage], stage_tx);
+        tma_load_2d(st + L.a_hi, &maps.a[seg], &full[stage], kc, (int)m_base);
+        if (csize == 1) {
+            tma_load_2d(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0);
+            if (TF32) tma_load_2d(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0);
+        } else if (crank == 0) {
+            tma_load_2d_mc(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0, cmask);
+            if (TF32) tma_load_2d_mc(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0, cmask);
         }
-        if (p.out) prefetch_tmap(&maps.out);
-        if (p.pre_out) prefetch_tmap(&maps.pre);
-        if (p.residual) prefetch_tmap(&maps.res);
-    }
-    if (warp == 1 && lane == 0) {
+    };
+    int prefilled = 0;  // producer thread: chunks requested before the setup barrier
+    if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], csize);
@@ -145,6 +152,21 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         mbar_init(accum_full, 1);
         mbar_init(res_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // The first ring of loads needs neither TMEM nor the per-column constants: request it NOW, so the ~1 us of DRAM
+        // latency runs under the rest of the setup (TMEM allocation, constant loads, the block-wide barrier) instead of
+        // after it.  (In a cluster the peers' barriers must exist first: no early start there.)
+        if (csize == 1) {
+            prefilled = total_chunks < p.stages ? total_chunks : p.stages;
+            for (int c = 0; c < prefilled; ++c) issue_chunk(c, c);
+        }
+        prefetch_tmap(&maps.w_hi[0]);
+        if (p.chunks[1]) {
+            prefetch_tmap(&maps.a[1]);
+            prefetch_tmap(&maps.w_hi[1]);
+        }
+        if (p.out) prefetch_tmap(&maps.out);
+        if (p.pre_out) prefetch_tmap(&maps.pre);
+        if (p.residual) prefetch_tmap(&maps.res);
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols)
@@ -169,23 +191,11 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t stage_tx = (uint32_t)(kTileM * CB + p.Npad * CB * (TF32 ? 2 : 1));
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int c = 0; c < total_chunks; ++c) {
-                const int seg = c >= p.chunks[0];
-                const int kc = (seg ? c - p.chunks[0] : c) * KPC;
+            int stage = prefilled == p.stages ? 0 : prefilled;
+            uint32_t phase = prefilled == p.stages ? 1u : 0u;
+            for (int c = prefilled; c < total_chunks; ++c) {
                 mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* st = smem + (size_t)stage * L.stage_bytes;
-                mbar_arrive_expect_tx(&full[stage], stage_tx);
-                tma_load_2d(st + L.a_hi, &maps.a[seg], &full[stage], kc, (int)m_base);
-                if (csize == 1) {
-                    tma_load_2d(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0);
-                    if (TF32) tma_load_2d(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0);
-                } else if (crank == 0) {
-                    tma_load_2d_mc(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0, cmask);
-                    if (TF32) tma_load_2d_mc(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0, cmask);
-                }
+                issue_chunk(c, stage);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
             if (p.residual) {
@@ -434,9 +444,11 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 const int c0 = g * 32;
                 const int ob = c0 / EPC, h = (c0 % EPC) / 32;
                 if (p.out && c0 % EPC == 0) box = acquire_box();
+                if (et == 0 && g < 4) PROBE(49 + 4 * g);  // box acquired
                 const uint8_t* rbox = smem + L.res + (size_t)ob * kTileM * kChunkBytes;
                 float v[32];
                 tmem_ld_wait(ra);
+                if (et == 0 && g < 4) PROBE(50 + 4 * g);  // TMEM values here
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
                 if (g + 1 < n32) tmem_ld32_issue(t_row + c0 + 32, ra);
@@ -491,10 +503,12 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                         }
                     }
                 }
+                if (et == 0 && g < 4) PROBE(51 + 4 * g);  // math done
                 if (p.out) {
                     stage_row(box, h * 32, v);
                     if ((c0 + 32) % EPC == 0) release_box(&maps.out, box, ob * EPC);
                 }
+                if (et == 0 && g < 4) PROBE(52 + 4 * g);  // staged + store issued
             }
         }
         if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);

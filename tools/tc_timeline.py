@@ -5,7 +5,7 @@ import ctypes, os, sys, torch
 REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path[:0] = [REPO, os.path.join(REPO, "deep-fem-uav-wing_b200")]
 from deep_fem_uav_wing.gnn import ops, _cabi
-dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(96, dtype=torch.int64, device="cuda")
 _cabi.lib.dfw_tc_set_probe.argtypes = [ctypes.c_void_p]
 assert _cabi.lib.dfw_tc_set_probe(dbg.data_ptr()) == 0
 n, H = 200000, 128
@@ -23,5 +23,7 @@ for dt in (torch.float32, torch.bfloat16):
     print(dt, "ns since the CTA's setup barrier")
     print("   TMA data landed (chunk c):", [rel(v) for v in d[21:41]])
     print("   MMA operands ready       :", [rel(v) for v in d[1:21]])
+    print("   kernel entry", rel(d[65]))
     print("   accum_full", rel(d[41]), "combined", rel(d[42]), "pass1", rel(d[43]), "pass2", rel(d[44]), "res_ready", rel(d[45]),
           "pass3", rel(d[46]), "stores_read", rel(d[47]), "exit", rel(d[48]))
+    print("   pass 3 per 32-column group (box acquired, TMEM values, math done, staged+store):", [rel(v) for v in d[49:65]])
