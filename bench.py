@@ -319,10 +319,12 @@ def main():
     # ---- roofline pass: same steps with per-launch CUDA events ---------------------------------
     prof_steps = min(steps, 8)
     ops.PROFILER = ops.KernelProfiler()
+    overlap, ops.OVERLAP_DW = ops.OVERLAP_DW, False  # every kernel alone on its stream while its duration is measured
     for i in range(prof_steps):
         train_step(resident[i % n_batches])
     summ = ops.PROFILER.summary()
     ops.PROFILER = None
+    ops.OVERLAP_DW = overlap
     pk = peaks()
     tot_ms = sum(r["ms"] for r in summ.values())
     kernels = {}

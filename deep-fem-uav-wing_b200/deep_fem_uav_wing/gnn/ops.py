@@ -6,6 +6,7 @@ arithmetic step of the GraphSAGE path is a hand-written sm_100a kernel reached t
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from dataclasses import dataclass, field
 
@@ -491,6 +492,19 @@ def _grad_to(param: torch.Tensor, g):
 # ----------------------------------------------------------------------------------------------
 # autograd Functions
 # ----------------------------------------------------------------------------------------------
+OVERLAP_DW = os.environ.get("DFW_OVERLAP_DW", "1") != "0"
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
+
 class SageConvFn(torch.autograd.Function):
     """SAGEConv forward/backward (mean aggregation + lin_l + lin_r), optionally with the
     model's LayerNorm -> ReLU -> dropout -> residual tail fused in (``model.py:90-95``)."""
@@ -530,10 +544,21 @@ class SageConvFn(torch.autograd.Function):
             # the epilogue backward also emits the column sums of g_y = lin_l's bias gradient
             g_y, dgamma, dbeta, _, _, dbl = epilogue_bwd(g_out, N, H, g_out, pre=pre, stats=stats, ln=(gamma, beta), relu=True,
                                                          dropout_p=ctx.dropout_p, seed=ctx.seed, want_bias_grad=ctx.has_bias)
-            dwl, dwr, _ = linear_bwd_weight(g_y, agg, x, want_bias=False)
         else:
             g_y = g_out
-            dwl, dwr, dbl = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias)
+        # The weight gradient and the input gradient both start from g_y and are independent of each other: the weight
+        # gradient runs on a side stream (fork after g_y, join before returning), so its CTAs fill the SMs that the
+        # partial last wave of the input-gradient kernels leaves idle (and vice versa).
+        main = torch.cuda.current_stream(g_y.device)
+        side = _side_stream(g_y.device) if (ctx.needs_input_grad[0] and OVERLAP_DW) else None
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dwl, dwr, db_ = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias and not ctx.fused_tail)
+        else:
+            dwl, dwr, db_ = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias and not ctx.fused_tail)
+        if not ctx.fused_tail:
+            dbl = db_
         g_x = None
         if ctx.needs_input_grad[0]:
             # dL/dx = A^T D^-1 (g_y W_l) + g_y W_r (+ g_out) = (A^T D^-1 g_y) W_l + g_y W_r (+ g_out): aggregate the
@@ -544,6 +569,8 @@ class SageConvFn(torch.autograd.Function):
             g_t = aggregate_scaled(rp_t, col_t, graph.inv_deg, g_y)
             g_x, _, _, _ = linear_fwd(g_t, wl, g_y, wr, residual=g_out if ctx.fused_tail else None, transpose_w=True,
                                       label="linear_bwd_input")
+        if side is not None:
+            main.wait_stream(side)
         return g_x, dwl, dbl, dwr, dgamma, dbeta, None, None, None, None, None
 
 
