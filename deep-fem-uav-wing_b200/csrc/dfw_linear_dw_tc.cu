@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_tc(const __grid_constant__ Dw
     constexpr uint32_t G_HI = 0, G_LO = OPER, A_HI = TF32 ? 2 * OPER : OPER, A_LO = 3 * OPER;
     constexpr int KSTEP_NODES = TF32 ? 8 : 16;              // UMMA_K
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment as an OFFSET into the shared window: the pointer keeps its address space, so the compiler
+    // emits LDS/STS instead of generic LD/ST for the converters and the epilogue staging
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE);
     uint64_t* empty = full + kDwMaxStages;
     uint64_t* conv = empty + kDwMaxStages;

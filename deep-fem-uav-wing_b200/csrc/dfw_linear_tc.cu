@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     constexpr int CB = TF32 ? 64 : 128;
     constexpr int KPC = CB / (int)sizeof(T);           // K elements per chunk
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment as an OFFSET into the shared window: the pointer keeps its address space, so the compiler
+    // emits LDS/STS instead of generic LD/ST for the converters and the epilogue staging
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int out_boxes = p.Hout / EPC;
     const Smem L = carve(TF32, p.Npad, p.stages, out_boxes);
     float* cvec = reinterpret_cast<float*>(smem + L.cvec);  // [4][256]: bias, gamma, beta, rowdot_w

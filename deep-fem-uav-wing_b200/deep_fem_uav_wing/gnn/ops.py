@@ -496,6 +496,33 @@ OVERLAP_DW = os.environ.get("DFW_OVERLAP_DW", "1") != "0"
 _SIDE_STREAMS: dict = {}
 
 
+class _fork_dw:
+    """``with _fork_dw(t, enabled):`` runs the body on the device's side stream, ordered after everything issued so far
+    on the current stream; ``join()`` makes the current stream wait for it.  (The weight gradient of a layer and its
+    input gradient are independent: side by side they fill each other's partial last waves.)"""
+
+    def __init__(self, like: torch.Tensor, enabled: bool):
+        self.main = torch.cuda.current_stream(like.device)
+        self.side = _side_stream(like.device) if (enabled and OVERLAP_DW) else None
+        self.ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+
+
 def _side_stream(device) -> torch.cuda.Stream:
     key = torch.device(device).index
     st = _SIDE_STREAMS.get(key)
@@ -546,16 +573,8 @@ class SageConvFn(torch.autograd.Function):
                                                          dropout_p=ctx.dropout_p, seed=ctx.seed, want_bias_grad=ctx.has_bias)
         else:
             g_y = g_out
-        # The weight gradient and the input gradient both start from g_y and are independent of each other: the weight
-        # gradient runs on a side stream (fork after g_y, join before returning), so its CTAs fill the SMs that the
-        # partial last wave of the input-gradient kernels leaves idle (and vice versa).
-        main = torch.cuda.current_stream(g_y.device)
-        side = _side_stream(g_y.device) if (ctx.needs_input_grad[0] and OVERLAP_DW) else None
-        if side is not None:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                dwl, dwr, db_ = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias and not ctx.fused_tail)
-        else:
+        fork = _fork_dw(g_y, ctx.needs_input_grad[0])
+        with fork:
             dwl, dwr, db_ = linear_bwd_weight(g_y, agg, x, want_bias=ctx.has_bias and not ctx.fused_tail)
         if not ctx.fused_tail:
             dbl = db_
@@ -569,8 +588,7 @@ class SageConvFn(torch.autograd.Function):
             g_t = aggregate_scaled(rp_t, col_t, graph.inv_deg, g_y)
             g_x, _, _, _ = linear_fwd(g_t, wl, g_y, wr, residual=g_out if ctx.fused_tail else None, transpose_w=True,
                                       label="linear_bwd_input")
-        if side is not None:
-            main.wait_stream(side)
+        fork.join()
         return g_x, dwl, dbl, dwr, dgamma, dbeta, None, None, None, None, None
 
 
@@ -600,11 +618,16 @@ class LinearFn(torch.autograd.Function):
                 raise RuntimeError("dfw_b200: ReLU/dropout backward needs out_features % 4 == 0")
             g_y, _, _, _, _, db = epilogue_bwd(g_out, N, H, g_out, act=act, relu=ctx.relu, dropout_p=ctx.dropout_p, seed=ctx.seed,
                                                want_bias_grad=ctx.has_bias)
-            dw, _, _ = linear_bwd_weight(g_y, x, None, want_bias=False)
+            want_db = False
         else:
-            g_y = g_out
-            dw, _, db = linear_bwd_weight(g_y, x, None, want_bias=ctx.has_bias)
+            g_y, db, want_db = g_out, None, ctx.has_bias
+        fork = _fork_dw(g_y, ctx.needs_input_grad[0])
+        with fork:
+            dw, _, db_ = linear_bwd_weight(g_y, x, None, want_bias=want_db)
+        if want_db:
+            db = db_
         g_x = linear_bwd_input(g_y, wc) if ctx.needs_input_grad[0] else None
+        fork.join()
         return g_x, dw, db, None, None, None
 
 
@@ -640,8 +663,11 @@ class DecoderTailFn(torch.autograd.Function):
         g_r = g_out.reshape(-1).float().contiguous()
         g_y, _, _, dw4, db4, db3 = epilogue_bwd(None, N, Hmid, hid, g_rowdot=g_r, rowdot_w=w4f, act=hid, relu=True,
                                                 dropout_p=ctx.dropout_p, seed=ctx.seed, want_bias_grad=ctx.has_b3)
-        dw3, _, _ = linear_bwd_weight(g_y, h, None, want_bias=False)
+        fork = _fork_dw(g_y, ctx.needs_input_grad[0])
+        with fork:
+            dw3, _, _ = linear_bwd_weight(g_y, h, None, want_bias=False)
         g_h = linear_bwd_input(g_y, w3c) if ctx.needs_input_grad[0] else None
+        fork.join()
         return g_h, dw3, db3, dw4.reshape(1, -1), (db4 if ctx.has_b4 else None), None, None
 
 
