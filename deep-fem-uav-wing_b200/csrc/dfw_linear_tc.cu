@@ -366,8 +366,10 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         // ---- pass 1: sum the accumulator regions (3xTF32: hi*hi [+ hi*hi] + cross, round-to-nearest), y = (acc + bias) *
         // row_scale written BACK to region 0 (passes 2 and 3 read finished values), row sum for LayerNorm, and the
         // pre-activation tensor ----
+        // Without LayerNorm and without a pre-activation output there is nothing to do between the passes: pass 3 sums the
+        // regions itself (input-gradient, encoder and decoder linears: one TMEM round trip less).
         const int regions = TF32 ? p.nacc + 1 : 1;
-        const bool y_in_tmem = TF32 || ln || p.pre_out;
+        const bool y_in_tmem = ln || p.pre_out;
         if (y_in_tmem) {
             float s = 0.f;
             uint32_t ra[32], rb[32];
@@ -376,7 +378,6 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             uint8_t* box = nullptr;
             for (int g = 0; g < n32; ++g) {
                 const int c0 = g * 32;
-                if (p.pre_out && c0 % EPC == 0) box = acquire_box();
                 float v[32];
                 tmem_ld_wait(ra);
                 if (regions > 1) {
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 for (int j = 0; j < 32; ++j) s += v[j];
                 tmem_st32_nowait(t_row + c0, v);
                 if (p.pre_out) {
+                    if (c0 % EPC == 0) box = acquire_box();  // as late as possible: the store that used this buffer has had the whole group's math to finish reading it
                     stage_row(box, c0 % EPC, v);
                     if ((c0 + 32) % EPC == 0) release_box(&maps.pre, box, c0 / EPC * EPC);
                 }
@@ -439,21 +441,36 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         if (et == 0) PROBE(45);  // residual tile in smem
         float dot = 0.f;
         {
-            uint32_t ra[32];
+            const bool sum_here = !y_in_tmem && regions > 1;
+            uint32_t ra[32], rb[32];
             tmem_ld32_issue(t_row, ra);
+            if (sum_here) tmem_ld32_issue(t_row + p.Npad, rb);
             uint8_t* box = nullptr;
             for (int g = 0; g < n32; ++g) {
                 const int c0 = g * 32;
                 const int ob = c0 / EPC, h = (c0 % EPC) / 32;
-                if (p.out && c0 % EPC == 0) box = acquire_box();
-                if (et == 0 && g < 4) PROBE(49 + 4 * g);  // box acquired
                 const uint8_t* rbox = smem + L.res + (size_t)ob * kTileM * kChunkBytes;
                 float v[32];
                 tmem_ld_wait(ra);
                 if (et == 0 && g < 4) PROBE(50 + 4 * g);  // TMEM values here
+                if (sum_here) {
+                    tmem_ld_wait(rb);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-                if (g + 1 < n32) tmem_ld32_issue(t_row + c0 + 32, ra);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+                    if (regions > 2) {
+                        float w[32];
+                        tmem_ld32(t_row + 2 * p.Npad + c0, w);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += w[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+                }
+                if (g + 1 < n32) {
+                    tmem_ld32_issue(t_row + c0 + 32, ra);
+                    if (sum_here) tmem_ld32_issue(t_row + p.Npad + c0 + 32, rb);
+                }
                 if (!y_in_tmem) finish_y(c0, v);
                 if (ln) {
 #pragma unroll
@@ -507,6 +524,8 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 }
                 if (et == 0 && g < 4) PROBE(51 + 4 * g);  // math done
                 if (p.out) {
+                    if (c0 % EPC == 0) box = acquire_box();
+                    if (et == 0 && g < 4) PROBE(49 + 4 * g);  // box acquired
                     stage_row(box, h * 32, v);
                     if ((c0 + 32) % EPC == 0) release_box(&maps.out, box, ob * EPC);
                 }
