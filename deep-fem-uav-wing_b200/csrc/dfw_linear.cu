@@ -522,50 +522,6 @@ namespace dfw {
 namespace {
 constexpr int kSmallKMax = 16;
 
-// out[n, c] = relu?(sum_k x[n,k] * w[c,k] + b[c]);  thread = (row, 4 output columns), weights in registers
-template <typename T>
-__global__ void __launch_bounds__(256) k_linear_smallk_fwd(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
-                                                            T* __restrict__ out, int64_t N, int K, int Hout, int relu) {
-    const int groups = Hout / 4;                       // column groups per row
-    const int rows_per_iter = blockDim.x / groups;     // rows handled by the block per iteration
-    const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
-    if (rl >= rows_per_iter) return;
-    float wr[4][kSmallKMax], b4[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        b4[j] = bias ? __ldg(bias + cg * 4 + j) : 0.f;
-#pragma unroll
-        for (int k = 0; k < kSmallKMax; ++k) wr[j][k] = k < K ? to_f32(w[(int64_t)(cg * 4 + j) * K + k]) : 0.f;
-    }
-    // four rows per iteration: their loads are issued together (one row at a time was a dependent load -> FMA -> store
-    // chain, 42 us for a 60 MB pass)
-    constexpr int U = 4;
-    const int64_t step = (int64_t)gridDim.x * rows_per_iter;
-    for (int64_t r0 = (int64_t)blockIdx.x * rows_per_iter + rl; r0 < N; r0 += step * U) {
-        float xv[U][kSmallKMax];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t r = r0 + u * step;
-#pragma unroll
-            for (int k = 0; k < kSmallKMax; ++k) xv[u][k] = (k < K && r < N) ? to_f32(x[r * K + k]) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t r = r0 + u * step;
-            if (r >= N) break;
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float a = b4[j];
-#pragma unroll
-                for (int k = 0; k < kSmallKMax; ++k) a = fmaf(xv[u][k], wr[j][k], a);
-                o[j] = relu ? fmaxf(a, 0.f) : a;
-            }
-            store_row4(out, r, (int64_t)Hout, cg * 4, (int64_t)Hout, o, true);
-        }
-    }
-}
-
 // partial dW[i, k] over the block's rows: thread = (output row i, k-slot), two-pass like the big kernels
 // dW for a tiny reduction width K (the encoder's first layer, K = 10): dW[i, k] = sum_rows g[row, i] * x[row, k].
 // A block owns a contiguous slice of rows; its 256 threads form 256/Hout row groups (thread = output feature i of
@@ -621,6 +577,129 @@ __global__ void __launch_bounds__(256) k_linear_smallk_dw(const T* __restrict__ 
         part[(int64_t)blockIdx.x * Hout * K + e] = t;
     }
 }
+// ---- tiled tiny-K kernels: x rows staged through shared memory ---------------------------------------------------
+// The kernels above read the K <= 16 inputs of a row with K scalar loads per thread (two rows per warp instruction):
+// 10-11 load instructions per 10-40 FMAs and a few KB in flight per SM - 47 us (forward) and 162 us (dW) for 59 MB
+// passes.  Here a block stages a tile of kSmallTile rows of x with coalesced loads (zero-padded to KP columns), every
+// thread owns four output features (one 16-byte vector of out / g) of kSmallTile / rows-per-pass rows of the tile and
+// reads its rows' inputs as KP/4 broadcast LDS.128.
+constexpr int kSmallTile = 64;
+
+template <typename T, int KP>
+__device__ __forceinline__ void smallk_stage(const T* __restrict__ x, float* xs, int64_t t0, int nr, int K) {
+    const int n = nr * K;
+    const T* src = x + t0 * K;
+    for (int e = threadIdx.x; e < n; e += 256) {
+        const int r = e / K, k = e - r * K;
+        xs[r * KP + k] = to_f32(src[e]);
+    }
+}
+
+template <typename T, int KP>
+__global__ void __launch_bounds__(256) k_smallk_fwd_tiled(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                                                           T* __restrict__ out, int64_t N, int K, int Hout, int relu) {
+    __shared__ __align__(16) float xs[kSmallTile * KP];
+    const int fq = Hout / 4;      // threads per row (<= 256)
+    const int rpi = 256 / fq;     // rows per pass
+    const int cq = threadIdx.x % fq, rl = threadIdx.x / fq;
+    const bool active = rl < rpi;
+    float wr[4][KP], b4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        b4[j] = bias ? __ldg(bias + cq * 4 + j) : 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) wr[j][k] = k < K ? to_f32(w[(int64_t)(cq * 4 + j) * K + k]) : 0.f;
+    }
+    for (int e = threadIdx.x; e < kSmallTile * KP; e += 256) xs[e] = 0.f;  // the padding columns stay zero
+    __syncthreads();
+    for (int64_t t0 = (int64_t)blockIdx.x * kSmallTile; t0 < N; t0 += (int64_t)gridDim.x * kSmallTile) {
+        const int nr = (int)min((int64_t)kSmallTile, N - t0);
+        smallk_stage<T, KP>(x, xs, t0, nr, K);
+        __syncthreads();
+        if (active) {
+            for (int r = rl; r < nr; r += rpi) {
+                float xv[KP];
+#pragma unroll
+                for (int k4 = 0; k4 < KP / 4; ++k4) {
+                    const float4 f = *reinterpret_cast<const float4*>(xs + r * KP + k4 * 4);
+                    xv[k4 * 4] = f.x; xv[k4 * 4 + 1] = f.y; xv[k4 * 4 + 2] = f.z; xv[k4 * 4 + 3] = f.w;
+                }
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = b4[j];
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) a = fmaf(xv[k], wr[j][k], a);
+                    o[j] = relu ? fmaxf(a, 0.f) : a;
+                }
+                store_row4(out, t0 + r, (int64_t)Hout, cq * 4, (int64_t)Hout, o, true);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// part[block][i * K + k] = sum over the block's tiles of g[row, i] * x[row, k]; fixed tile -> block assignment and a
+// fixed-order reduction over the row lanes: bit-reproducible.  Reduced over blocks by k_smallk_dw_reduce.
+template <typename T, int KP>
+__global__ void __launch_bounds__(256) k_smallk_dw_tiled(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ part,
+                                                          int64_t N, int K, int Hout) {
+    __shared__ __align__(16) float xs[kSmallTile * KP];
+    __shared__ float s_red[256 * KP];
+    const int fq = Hout / 4;      // threads per row (Hout <= 256: <= 64)
+    const int rpi = 256 / fq;     // row lanes (>= 4)
+    const int cq = threadIdx.x % fq, rl = threadIdx.x / fq;
+    const bool active = rl < rpi;
+    float acc[4][KP];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[j][k] = 0.f;
+    for (int e = threadIdx.x; e < kSmallTile * KP; e += 256) xs[e] = 0.f;
+    __syncthreads();
+    for (int64_t t0 = (int64_t)blockIdx.x * kSmallTile; t0 < N; t0 += (int64_t)gridDim.x * kSmallTile) {
+        const int nr = (int)min((int64_t)kSmallTile, N - t0);
+        smallk_stage<T, KP>(x, xs, t0, nr, K);
+        __syncthreads();
+        if (active) {
+            for (int r = rl; r < nr; r += rpi) {
+                float gv[4];
+                load_row4(g, t0 + r, (int64_t)Hout, cq * 4, (int64_t)Hout, gv, true);
+#pragma unroll
+                for (int k4 = 0; k4 < KP / 4; ++k4) {
+                    const float4 f = *reinterpret_cast<const float4*>(xs + r * KP + k4 * 4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j][k4 * 4] = fmaf(gv[j], f.x, acc[j][k4 * 4]);
+                        acc[j][k4 * 4 + 1] = fmaf(gv[j], f.y, acc[j][k4 * 4 + 1]);
+                        acc[j][k4 * 4 + 2] = fmaf(gv[j], f.z, acc[j][k4 * 4 + 2]);
+                        acc[j][k4 * 4 + 3] = fmaf(gv[j], f.w, acc[j][k4 * 4 + 3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // sum the row lanes, one of the four features per round (keeps the scratch at 256 * KP floats)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) s_red[(rl * fq + cq) * KP + k] = acc[j][k];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < fq * KP; e += 256) {
+            const int c = e / KP, k = e - c * KP;
+            if (k < K) {
+                float t = 0.f;
+                for (int q = 0; q < rpi; ++q) t += s_red[(q * fq + c) * KP + k];
+                part[(int64_t)blockIdx.x * Hout * K + (int64_t)(c * 4 + j) * K + k] = t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_smallk_dw_reduce(const float* __restrict__ part, int blocks, int total, float* __restrict__ dw,
                                                            int accumulate) {
     const int lane = threadIdx.x & 31;
@@ -677,15 +756,19 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
     if (!force_simt() && !a2 && k1 <= kSmallKMax && Hout % 4 == 0 && Hout <= 1024 && out && !pre_out && !rowdot_out &&
         !(flags & ~DFW_EP_RELU) && aligned16(out)) {
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-        const int groups = (int)(Hout / 4);
-        const int threads = std::max(groups, 256 / groups * groups);
-        const int rows_per_iter = threads / groups;
-        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((N + rows_per_iter - 1) / rows_per_iter, (int64_t)kNumSMs * 8));
-        if (dtype == DFW_F32)
-            k_linear_smallk_fwd<float><<<blocks, threads, 0, st>>>((const float*)a1, (const float*)w1, bias, (float*)out, N, (int)k1, (int)Hout, flags & DFW_EP_RELU);
-        else
-            k_linear_smallk_fwd<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)a1, (const __nv_bfloat16*)w1, bias, (__nv_bfloat16*)out, N,
-                                                                        (int)k1, (int)Hout, flags & DFW_EP_RELU);
+        const int64_t tiles = (N + kSmallTile - 1) / kSmallTile;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)kNumSMs * 6));
+#define DFW_SK_FWD(TT, KPV)                                                                                              \
+    k_smallk_fwd_tiled<TT, KPV><<<blocks, 256, 0, st>>>((const TT*)a1, (const TT*)w1, bias, (TT*)out, N, (int)k1, (int)Hout, \
+                                                   flags & DFW_EP_RELU)
+#define DFW_SK_FWD_K(TT)                                                                                                 \
+    do {                                                                                                                 \
+    if (k1 <= 4) DFW_SK_FWD(TT, 4); else if (k1 <= 8) DFW_SK_FWD(TT, 8); else if (k1 <= 12) DFW_SK_FWD(TT, 12);       \
+    else DFW_SK_FWD(TT, 16);                                                                                         \
+    } while (0)
+        if (dtype == DFW_F32) DFW_SK_FWD_K(float); else DFW_SK_FWD_K(__nv_bfloat16);
+#undef DFW_SK_FWD_K
+#undef DFW_SK_FWD
         DFW_LAUNCH_CHECK();
         return 0;
     }
@@ -822,6 +905,23 @@ extern "C" int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1
     if (N > 0 && !force_simt() && !a2 && !dbias && k1 <= kSmallKMax && Hout <= 256) {
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((N + 255) / 256, (int64_t)kNumSMs * 4));
         const size_t need = sizeof(float) * (size_t)blocks * Hout * k1;
+        if (ws && ws_bytes >= need && Hout % 4 == 0 && aligned16(g_y)) {
+            float* part = reinterpret_cast<float*>(ws);
+#define DFW_SK_DW(TT, KPV) k_smallk_dw_tiled<TT, KPV><<<blocks, 256, 0, s>>>((const TT*)g_y, (const TT*)a1, part, N, (int)k1, (int)Hout)
+#define DFW_SK_DW_K(TT)                                                                                                 \
+    do {                                                                                                                \
+        if (k1 <= 4) DFW_SK_DW(TT, 4); else if (k1 <= 8) DFW_SK_DW(TT, 8); else if (k1 <= 12) DFW_SK_DW(TT, 12);         \
+        else DFW_SK_DW(TT, 16);                                                                                         \
+    } while (0)
+            if (dtype == DFW_F32) DFW_SK_DW_K(float); else DFW_SK_DW_K(__nv_bfloat16);
+#undef DFW_SK_DW_K
+#undef DFW_SK_DW
+            DFW_LAUNCH_CHECK();
+            const int total = (int)(Hout * k1);
+            k_smallk_dw_reduce<<<(total * 32 + 255) / 256, 256, 0, s>>>(part, blocks, total, dw1, accumulate);
+            DFW_LAUNCH_CHECK();
+            return 0;
+        }
         if (ws && ws_bytes >= need) {
             float* part = reinterpret_cast<float*>(ws);
             const size_t red_bytes = sizeof(float) * (size_t)(256 / Hout) * Hout * k1;  // <= 16 KB

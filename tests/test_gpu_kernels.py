@@ -225,6 +225,28 @@ def test_linear_transposed_weights_equal_pretransposed(ops, kin, hout, dtype):
     assert rel_max(c.double(), g_t.double() @ wl.double()) < (TOL_FP32 if dtype == torch.float32 else TOL_BF16)
 
 
+@pytest.mark.parametrize("k,hout,n", [(10, 64, 200003), (3, 64, 777), (8, 128, 4099), (16, 256, 1000), (12, 4, 65), (10, 64, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tiny_k_linear_forward_and_weight_gradient(ops, k, hout, n, dtype):
+    """The encoder's first layer (``Linear(10, 64)``, model.py:53): tiled tiny-K kernels, forward and dW."""
+    torch.manual_seed(k * 1000 + hout)
+    dev = "cuda"
+    x = torch.randn(n, k, device=dev).to(dtype)
+    w = (torch.randn(hout, k, device=dev) / k**0.5).to(dtype)
+    b = torch.randn(hout, device=dev)
+    tol = TOL_FP32 if dtype == torch.float32 else TOL_BF16
+    for relu in (True, False):
+        out, _, _, _ = ops.linear_fwd(x, w, bias=b, relu=relu)
+        ref = x.double() @ w.double().T + b.double()
+        ref = torch.relu(ref) if relu else ref
+        assert out.shape == (n, hout) and rel_max(out.double(), ref) < tol
+    g = torch.randn(n, hout, device=dev).to(dtype)
+    dw, _, _ = ops.linear_bwd_weight(g, x, None, want_bias=False)
+    assert dw.dtype == torch.float32 and rel_l2(dw.double(), g.double().T @ x.double()) < (TOL_FP32 if dtype == torch.float32 else 1e-4)
+    dw2, _, _ = ops.linear_bwd_weight(g, x, None, want_bias=False)
+    assert torch.equal(dw, dw2)  # fixed tile -> block assignment, fixed-order reductions
+
+
 def test_masked_mse_matches_reference_fixture(ops):
     from helpers import load_golden
 
