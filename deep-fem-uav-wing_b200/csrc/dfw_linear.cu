@@ -583,22 +583,40 @@ __global__ void __launch_bounds__(256) k_linear_smallk_dw(const T* __restrict__ 
 // passes.  Here a block stages a tile of kSmallTile rows of x with coalesced loads (zero-padded to KP columns), every
 // thread owns four output features (one 16-byte vector of out / g) of kSmallTile / rows-per-pass rows of the tile and
 // reads its rows' inputs as KP/4 broadcast LDS.128.
-constexpr int kSmallTile = 64;
+constexpr int kSmallTile = 128;
 
+// The x tile of the NEXT iteration is fetched into registers before the current tile is worked on and written to the
+// other shared-memory buffer afterwards: one barrier per tile, global latency under the arithmetic.
 template <typename T, int KP>
-__device__ __forceinline__ void smallk_stage(const T* __restrict__ x, float* xs, int64_t t0, int nr, int K) {
-    const int n = nr * K;
-    const T* src = x + t0 * K;
-    for (int e = threadIdx.x; e < n; e += 256) {
-        const int r = e / K, k = e - r * K;
-        xs[r * KP + k] = to_f32(src[e]);
+struct SmallKStage {
+    static constexpr int XR = (kSmallTile * KP + 255) / 256;  // staged elements per thread
+    float xr[XR];
+    __device__ __forceinline__ void fetch(const T* __restrict__ x, int64_t t0, int nr, int K) {
+        const int n = nr * K;
+        const T* src = x + t0 * K;
+#pragma unroll
+        for (int i = 0; i < XR; ++i) {
+            const int e = threadIdx.x + i * 256;
+            xr[i] = e < n ? to_f32(src[e]) : 0.f;
+        }
     }
-}
+    __device__ __forceinline__ void commit(float* xs, int nr, int K) const {
+        const int n = nr * K;
+#pragma unroll
+        for (int i = 0; i < XR; ++i) {
+            const int e = threadIdx.x + i * 256;
+            if (e < n) {
+                const int r = e / K, k = e - r * K;
+                xs[r * KP + k] = xr[i];
+            }
+        }
+    }
+};
 
 template <typename T, int KP>
-__global__ void __launch_bounds__(256) k_smallk_fwd_tiled(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
-                                                           T* __restrict__ out, int64_t N, int K, int Hout, int relu) {
-    __shared__ __align__(16) float xs[kSmallTile * KP];
+__global__ void __launch_bounds__(256, 3) k_smallk_fwd_tiled(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                                                              T* __restrict__ out, int64_t N, int K, int Hout, int relu) {
+    __shared__ __align__(16) float xs[2][kSmallTile * KP];
     const int fq = Hout / 4;      // threads per row (<= 256)
     const int rpi = 256 / fq;     // rows per pass
     const int cq = threadIdx.x % fq, rl = threadIdx.x / fq;
@@ -610,18 +628,27 @@ __global__ void __launch_bounds__(256) k_smallk_fwd_tiled(const T* __restrict__ 
 #pragma unroll
         for (int k = 0; k < KP; ++k) wr[j][k] = k < K ? to_f32(w[(int64_t)(cq * 4 + j) * K + k]) : 0.f;
     }
-    for (int e = threadIdx.x; e < kSmallTile * KP; e += 256) xs[e] = 0.f;  // the padding columns stay zero
+    for (int e = threadIdx.x; e < 2 * kSmallTile * KP; e += 256) (&xs[0][0])[e] = 0.f;  // the padding columns stay zero
+    const int64_t stride = (int64_t)gridDim.x * kSmallTile;
+    int64_t t0 = (int64_t)blockIdx.x * kSmallTile;
+    SmallKStage<T, KP> st;
+    int buf = 0;
+    if (t0 < N) st.fetch(x, t0, (int)min((int64_t)kSmallTile, N - t0), K);
     __syncthreads();
-    for (int64_t t0 = (int64_t)blockIdx.x * kSmallTile; t0 < N; t0 += (int64_t)gridDim.x * kSmallTile) {
+    if (t0 < N) st.commit(xs[0], (int)min((int64_t)kSmallTile, N - t0), K);
+    __syncthreads();
+    for (; t0 < N; t0 += stride, buf ^= 1) {
         const int nr = (int)min((int64_t)kSmallTile, N - t0);
-        smallk_stage<T, KP>(x, xs, t0, nr, K);
-        __syncthreads();
+        const int64_t t1 = t0 + stride;
+        const int nr1 = t1 < N ? (int)min((int64_t)kSmallTile, N - t1) : 0;
+        if (nr1) st.fetch(x, t1, nr1, K);
         if (active) {
+            const float* xt = xs[buf];
             for (int r = rl; r < nr; r += rpi) {
                 float xv[KP];
 #pragma unroll
                 for (int k4 = 0; k4 < KP / 4; ++k4) {
-                    const float4 f = *reinterpret_cast<const float4*>(xs + r * KP + k4 * 4);
+                    const float4 f = *reinterpret_cast<const float4*>(xt + r * KP + k4 * 4);
                     xv[k4 * 4] = f.x; xv[k4 * 4 + 1] = f.y; xv[k4 * 4 + 2] = f.z; xv[k4 * 4 + 3] = f.w;
                 }
                 float o[4];
@@ -635,6 +662,7 @@ __global__ void __launch_bounds__(256) k_smallk_fwd_tiled(const T* __restrict__ 
                 store_row4(out, t0 + r, (int64_t)Hout, cq * 4, (int64_t)Hout, o, true);
             }
         }
+        if (nr1) st.commit(xs[buf ^ 1], nr1, K);
         __syncthreads();
     }
 }
@@ -642,9 +670,9 @@ __global__ void __launch_bounds__(256) k_smallk_fwd_tiled(const T* __restrict__ 
 // part[block][i * K + k] = sum over the block's tiles of g[row, i] * x[row, k]; fixed tile -> block assignment and a
 // fixed-order reduction over the row lanes: bit-reproducible.  Reduced over blocks by k_smallk_dw_reduce.
 template <typename T, int KP>
-__global__ void __launch_bounds__(256) k_smallk_dw_tiled(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ part,
-                                                          int64_t N, int K, int Hout) {
-    __shared__ __align__(16) float xs[kSmallTile * KP];
+__global__ void __launch_bounds__(256, 2) k_smallk_dw_tiled(const T* __restrict__ g, const T* __restrict__ x, float* __restrict__ part,
+                                                             int64_t N, int K, int Hout) {
+    __shared__ __align__(16) float xs[2][kSmallTile * KP];
     __shared__ float s_red[256 * KP];
     const int fq = Hout / 4;      // threads per row (Hout <= 256: <= 64)
     const int rpi = 256 / fq;     // row lanes (>= 4)
@@ -655,29 +683,52 @@ __global__ void __launch_bounds__(256) k_smallk_dw_tiled(const T* __restrict__ g
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < KP; ++k) acc[j][k] = 0.f;
-    for (int e = threadIdx.x; e < kSmallTile * KP; e += 256) xs[e] = 0.f;
+    for (int e = threadIdx.x; e < 2 * kSmallTile * KP; e += 256) (&xs[0][0])[e] = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * kSmallTile;
+    int64_t t0 = (int64_t)blockIdx.x * kSmallTile;
+    SmallKStage<T, KP> st;
+    int buf = 0;
+    if (t0 < N) st.fetch(x, t0, (int)min((int64_t)kSmallTile, N - t0), K);
     __syncthreads();
-    for (int64_t t0 = (int64_t)blockIdx.x * kSmallTile; t0 < N; t0 += (int64_t)gridDim.x * kSmallTile) {
+    if (t0 < N) st.commit(xs[0], (int)min((int64_t)kSmallTile, N - t0), K);
+    __syncthreads();
+    for (; t0 < N; t0 += stride, buf ^= 1) {
         const int nr = (int)min((int64_t)kSmallTile, N - t0);
-        smallk_stage<T, KP>(x, xs, t0, nr, K);
-        __syncthreads();
+        const int64_t t1 = t0 + stride;
+        const int nr1 = t1 < N ? (int)min((int64_t)kSmallTile, N - t1) : 0;
+        if (nr1) st.fetch(x, t1, nr1, K);
         if (active) {
-            for (int r = rl; r < nr; r += rpi) {
-                float gv[4];
-                load_row4(g, t0 + r, (int64_t)Hout, cq * 4, (int64_t)Hout, gv, true);
+            const float* xt = xs[buf];
+            constexpr int U = 8;  // rows of g in flight per thread
+            for (int r = rl; r < nr; r += U * rpi) {
+                float gv[U][4];
 #pragma unroll
-                for (int k4 = 0; k4 < KP / 4; ++k4) {
-                    const float4 f = *reinterpret_cast<const float4*>(xs + r * KP + k4 * 4);
+                for (int u = 0; u < U; ++u) {
+                    const int rr = r + u * rpi;
+                    if (rr < nr) {
+                        load_row4(g, t0 + rr, (int64_t)Hout, cq * 4, (int64_t)Hout, gv[u], true);
+                    } else {
+                        gv[u][0] = gv[u][1] = gv[u][2] = gv[u][3] = 0.f;
+                    }
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        acc[j][k4 * 4] = fmaf(gv[j], f.x, acc[j][k4 * 4]);
-                        acc[j][k4 * 4 + 1] = fmaf(gv[j], f.y, acc[j][k4 * 4 + 1]);
-                        acc[j][k4 * 4 + 2] = fmaf(gv[j], f.z, acc[j][k4 * 4 + 2]);
-                        acc[j][k4 * 4 + 3] = fmaf(gv[j], f.w, acc[j][k4 * 4 + 3]);
+                for (int u = 0; u < U; ++u) {
+                    const int rr = min(r + u * rpi, nr - 1);  // rows past the tile carry g = 0
+#pragma unroll
+                    for (int k4 = 0; k4 < KP / 4; ++k4) {
+                        const float4 f = *reinterpret_cast<const float4*>(xt + rr * KP + k4 * 4);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            acc[j][k4 * 4] = fmaf(gv[u][j], f.x, acc[j][k4 * 4]);
+                            acc[j][k4 * 4 + 1] = fmaf(gv[u][j], f.y, acc[j][k4 * 4 + 1]);
+                            acc[j][k4 * 4 + 2] = fmaf(gv[u][j], f.z, acc[j][k4 * 4 + 2]);
+                            acc[j][k4 * 4 + 3] = fmaf(gv[u][j], f.w, acc[j][k4 * 4 + 3]);
+                        }
                     }
                 }
             }
         }
+        if (nr1) st.commit(xs[buf ^ 1], nr1, K);
         __syncthreads();
     }
     // sum the row lanes, one of the four features per round (keeps the scratch at 256 * KP floats)
@@ -757,7 +808,7 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
         !(flags & ~DFW_EP_RELU) && aligned16(out)) {
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
         const int64_t tiles = (N + kSmallTile - 1) / kSmallTile;
-        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)kNumSMs * 6));
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)kNumSMs * 3));  // 3 resident blocks per SM
 #define DFW_SK_FWD(TT, KPV)                                                                                              \
     k_smallk_fwd_tiled<TT, KPV><<<blocks, 256, 0, st>>>((const TT*)a1, (const TT*)w1, bias, (TT*)out, N, (int)k1, (int)Hout, \
                                                    flags & DFW_EP_RELU)
@@ -903,9 +954,10 @@ extern "C" int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1
         return 0;
     }
     if (N > 0 && !force_simt() && !a2 && !dbias && k1 <= kSmallKMax && Hout <= 256) {
-        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((N + 255) / 256, (int64_t)kNumSMs * 4));
+        int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((N + 255) / 256, (int64_t)kNumSMs * 4));
         const size_t need = sizeof(float) * (size_t)blocks * Hout * k1;
         if (ws && ws_bytes >= need && Hout % 4 == 0 && aligned16(g_y)) {
+            blocks = (int)std::max<int64_t>(1, std::min<int64_t>((N + kSmallTile - 1) / kSmallTile, (int64_t)kNumSMs * 2));  // 2 resident blocks per SM
             float* part = reinterpret_cast<float*>(ws);
 #define DFW_SK_DW(TT, KPV) k_smallk_dw_tiled<TT, KPV><<<blocks, 256, 0, s>>>((const TT*)g_y, (const TT*)a1, part, N, (int)k1, (int)Hout)
 #define DFW_SK_DW_K(TT)                                                                                                 \
