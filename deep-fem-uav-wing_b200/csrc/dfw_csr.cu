@@ -53,7 +53,9 @@ CsrWs carve(void* ws, int64_t E, int64_t N) {
 }
 
 __global__ void k_count(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t E,
-                        int64_t N, int32_t* __restrict__ cnt_plus1, int32_t* __restrict__ status) {
+                        int64_t N, int32_t* __restrict__ cnt_plus1, int32_t* __restrict__ status,
+        const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // dfw_csr_transpose: the graph turned out to be symmetric, nothing to build
     int bad = 0;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = rows[e], c = cols[e];
@@ -92,7 +94,9 @@ __device__ __forceinline__ int block_inclusive_scan(int v, int* smem /*32 ints*/
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_scan_partial(const int32_t* __restrict__ a, int64_t n,
-                                                                int32_t* __restrict__ blocksums) {
+                                                                int32_t* __restrict__ blocksums,
+        const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // dfw_csr_transpose: the graph turned out to be symmetric, nothing to build
     __shared__ int sm[32];
     int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
     int s = 0;
@@ -103,7 +107,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_partial(const int32_t* __
     if (threadIdx.x == kScanThreads - 1) blocksums[blockIdx.x] = incl;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_blocksums(int32_t* __restrict__ blocksums, int nblk) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_blocksums(int32_t* __restrict__ blocksums, int nblk,
+        const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // dfw_csr_transpose: the graph turned out to be symmetric, nothing to build
     __shared__ int sm[32];
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -125,7 +131,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_blocksums(int32_t* __rest
 __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int32_t* __restrict__ a, int64_t n /*N+1*/,
                                                               const int32_t* __restrict__ blocksums,
                                                               int32_t* __restrict__ cursor, float* __restrict__ inv_deg,
-                                                              int32_t* __restrict__ status) {
+                                                              int32_t* __restrict__ status,
+        const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // dfw_csr_transpose: the graph turned out to be symmetric, nothing to build
     __shared__ int sm[32];
     int64_t base = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
     int v[kScanItems];
@@ -154,7 +162,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int32_t* __restrict
 }
 
 __global__ void k_fill(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t E, int64_t N,
-                       int32_t* __restrict__ cursor, uint64_t* __restrict__ keys) {
+                       int32_t* __restrict__ cursor, uint64_t* __restrict__ keys,
+        const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // dfw_csr_transpose: the graph turned out to be symmetric, nothing to build
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = rows[e], c = cols[e];
         if ((uint64_t)r < (uint64_t)N && (uint64_t)c < (uint64_t)N) {
@@ -168,7 +178,9 @@ __global__ void k_fill(const int64_t* __restrict__ rows, const int64_t* __restri
 __global__ void __launch_bounds__(256) k_sort_rows_warp(const int32_t* __restrict__ rowptr, int64_t N,
                                                          const uint64_t* __restrict__ keys, int32_t* __restrict__ col,
                                                          int32_t* __restrict__ perm, int32_t* __restrict__ worklist,
-                                                         int32_t* __restrict__ counters) {
+                                                         int32_t* __restrict__ counters,
+        const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // dfw_csr_transpose: the graph turned out to be symmetric, nothing to build
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += warps) {
@@ -223,7 +235,9 @@ __device__ __forceinline__ void bitonic_ascending(Ptr a, int n) {
 __global__ void __launch_bounds__(256) k_sort_rows_big(const int32_t* __restrict__ rowptr, uint64_t* __restrict__ keys,
                                                         int32_t* __restrict__ col, int32_t* __restrict__ perm,
                                                         const int32_t* __restrict__ worklist,
-                                                        const int32_t* __restrict__ counters) {
+                                                        const int32_t* __restrict__ counters,
+        const int32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;  // dfw_csr_transpose: the graph turned out to be symmetric, nothing to build
     __shared__ uint64_t sk[kBigRowSmemKeys];
     const int nwork = counters[0];
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -261,7 +275,8 @@ extern "C" size_t dfw_csr_ws_bytes(int64_t E, int64_t N) {
 
 namespace dfw {
 static int csr_build_impl(const int64_t* edge_index, int64_t E, int64_t N, int by_src, int32_t* rowptr, int32_t* col,
-                          int32_t* perm, float* inv_deg, int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
+                          int32_t* perm, float* inv_deg, int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream,
+                          const int32_t* gate = nullptr);
 }
 
 extern "C" int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src, int32_t* rowptr,
@@ -272,7 +287,8 @@ extern "C" int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, in
 
 namespace dfw {
 static int csr_build_impl(const int64_t* edge_index, int64_t E, int64_t N, int by_src, int32_t* rowptr, int32_t* col,
-                          int32_t* perm, float* inv_deg, int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream) {
+                          int32_t* perm, float* inv_deg, int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream,
+                          const int32_t* gate) {
     DFW_REQUIRE(E >= 0 && N >= 0, "dfw_csr_build: negative size (E=%lld, N=%lld)", (long long)E, (long long)N);
     DFW_REQUIRE(E < 2147483647LL && N < 2147483647LL, "dfw_csr_build: E and N must be < 2^31 (E=%lld, N=%lld)",
                 (long long)E, (long long)N);
@@ -291,30 +307,88 @@ static int csr_build_impl(const int64_t* edge_index, int64_t E, int64_t N, int b
     const int threads = 256;
     const int grid_e = (int)std::max<int64_t>(1, std::min<int64_t>((E + threads - 1) / threads, (int64_t)kNumSMs * 16));
     if (E > 0) {
-        k_count<<<grid_e, threads, 0, s>>>(rows, cols, E, N, rowptr, status);
+        k_count<<<grid_e, threads, 0, s>>>(rows, cols, E, N, rowptr, status, gate);
         DFW_LAUNCH_CHECK();
     }
     const int64_t n1 = N + 1;
     const int nblk = (int)((n1 + kScanChunk - 1) / kScanChunk);
-    k_scan_partial<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, w.blocksums);
+    k_scan_partial<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, w.blocksums, gate);
     DFW_LAUNCH_CHECK();
-    k_scan_blocksums<<<1, kScanThreads, 0, s>>>(w.blocksums, nblk);
+    k_scan_blocksums<<<1, kScanThreads, 0, s>>>(w.blocksums, nblk, gate);
     DFW_LAUNCH_CHECK();
-    k_scan_apply<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, w.blocksums, w.cursor, inv_deg, status);
+    k_scan_apply<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, w.blocksums, w.cursor, inv_deg, status, gate);
     DFW_LAUNCH_CHECK();
     if (E > 0) {
-        k_fill<<<grid_e, threads, 0, s>>>(rows, cols, E, N, w.cursor, w.keys);
+        k_fill<<<grid_e, threads, 0, s>>>(rows, cols, E, N, w.cursor, w.keys, gate);
         DFW_LAUNCH_CHECK();
         const int64_t warps_per_block = threads / 32;
         const int grid_r = (int)std::max<int64_t>(1, std::min<int64_t>((N + warps_per_block - 1) / warps_per_block, (int64_t)kNumSMs * 64));
-        k_sort_rows_warp<<<grid_r, threads, 0, s>>>(rowptr, N, w.keys, col, perm, w.worklist, w.counters);
+        k_sort_rows_warp<<<grid_r, threads, 0, s>>>(rowptr, N, w.keys, col, perm, w.worklist, w.counters, gate);
         DFW_LAUNCH_CHECK();
-        k_sort_rows_big<<<kNumSMs * 2, 256, 0, s>>>(rowptr, w.keys, col, perm, w.worklist, w.counters);
+        k_sort_rows_big<<<kNumSMs * 2, 256, 0, s>>>(rowptr, w.keys, col, perm, w.worklist, w.counters, gate);
         DFW_LAUNCH_CHECK();
     }
     return 0;
 }
 }  // namespace dfw
+
+// ---- transposed CSR (rows = source) for the backward gather -------------------------------------------------
+// Mesh graphs carry both directions of every edge (reference gnn/dataset.py:55-58), and then the CSR by source IS the
+// CSR by destination.  dfw_csr_transpose checks that on the device (every edge (s -> d) of a duplicate-free CSR has its
+// mirror (d -> s): one binary search per edge in the L2-resident col array) and either copies the CSR or runs the
+// general build; the decision never leaves the device (the general build's kernels are gated on the flag), so the
+// call is capturable in a CUDA graph and costs no host synchronisation.
+namespace dfw {
+namespace {
+__global__ void __launch_bounds__(256) k_sym_check(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N,
+                                                    int32_t* __restrict__ asym) {
+    for (int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; d < N; d += (int64_t)gridDim.x * blockDim.x) {
+        const int beg = rowptr[d], end = rowptr[d + 1];
+        bool bad = false;
+        for (int e = beg; e < end && !bad; ++e) {
+            const int s = col[e];
+            if (e + 1 < end && col[e + 1] == s) bad = true;  // duplicate edge: multiplicities would have to match too
+            int lo = rowptr[s], hi = rowptr[s + 1];           // is d among the sources of row s ?
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (col[mid] < (int)d) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= rowptr[s + 1] || col[lo] != (int)d) bad = true;
+        }
+        if (bad) *asym = 1;
+    }
+}
+__global__ void __launch_bounds__(256) k_copy_if_symmetric(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N,
+                                                            int64_t E, int32_t* __restrict__ rowptr_t, int32_t* __restrict__ col_t,
+                                                            const int32_t* __restrict__ asym) {
+    if (*asym) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= N; i += stride) rowptr_t[i] = rowptr[i];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += stride) col_t[i] = col[i];
+}
+}  // namespace
+}  // namespace dfw
+
+extern "C" int dfw_csr_transpose(const int64_t* edge_index, int64_t E, int64_t N, const int32_t* rowptr, const int32_t* col,
+                                 int32_t* rowptr_t, int32_t* col_t, int32_t* status, void* ws, size_t ws_bytes,
+                                 dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(E >= 0 && N >= 0, "dfw_csr_transpose: negative size (E=%lld, N=%lld)", (long long)E, (long long)N);
+    DFW_REQUIRE(rowptr && rowptr_t && status && ((col && col_t) || E == 0), "dfw_csr_transpose: null pointer");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    DFW_CUDA(cudaMemsetAsync(status + 2, 0, sizeof(int32_t), s));
+    if (N > 0) {
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((N + 255) / 256, (int64_t)kNumSMs * 16));
+        k_sym_check<<<grid, 256, 0, s>>>(rowptr, col, N, status + 2);
+        DFW_LAUNCH_CHECK();
+    }
+    const int rc = csr_build_impl(edge_index, E, N, 1, rowptr_t, col_t, nullptr, nullptr, status, ws, ws_bytes, stream, status + 2);
+    if (rc) return rc;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((std::max(E, N + 1) + 255) / 256, (int64_t)kNumSMs * 8));
+    k_copy_if_symmetric<<<grid, 256, 0, s>>>(rowptr, col, N, E, rowptr_t, col_t, status + 2);
+    DFW_LAUNCH_CHECK();
+    return 0;
+}
 
 // =============================================================================================
 // (f1) Graph construction from triangle faces, on the device.
@@ -512,11 +586,11 @@ extern "C" int dfw_faces_to_csr(const int64_t* faces, int64_t F, const int64_t* 
     DFW_CUDA(cudaMemsetAsync(status + 1, 0, sizeof(int32_t), s));
     const int64_t n1 = N + 1;
     const int nblk = (int)((n1 + kScanChunk - 1) / kScanChunk);
-    k_scan_partial<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, cw.blocksums);
+    k_scan_partial<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, cw.blocksums, nullptr);
     DFW_LAUNCH_CHECK();
-    k_scan_blocksums<<<1, kScanThreads, 0, s>>>(cw.blocksums, nblk);
+    k_scan_blocksums<<<1, kScanThreads, 0, s>>>(cw.blocksums, nblk, nullptr);
     DFW_LAUNCH_CHECK();
-    k_scan_apply<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, cw.blocksums, cw.cursor, inv_deg, status);
+    k_scan_apply<<<nblk, kScanThreads, 0, s>>>(rowptr, n1, cw.blocksums, cw.cursor, inv_deg, status, nullptr);
     DFW_LAUNCH_CHECK();
     if (N > 0 && F > 0) {
         k_unique_fill<<<grid_r, threads, 0, s>>>(w.rowptr0, w.col0, rowptr, N, col, edge_index, E0);

@@ -22,6 +22,8 @@ SIGNATURES = {
     "dfw_csr_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "dfw_csr_build": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
+    "dfw_csr_transpose": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]),
     "dfw_faces_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "dfw_faces_to_csr": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -124,13 +124,13 @@ class CSRGraph:
     col_t: torch.Tensor | None = None
     _pending: list = field(default_factory=list)
     skipped_faces: torch.Tensor | None = None
+    status_t: torch.Tensor | None = None  # int32 [3] of dfw_csr_transpose ([2] = 1: the graph was not symmetric)
 
     def transpose(self):
         if self.rowptr_t is None:
             if self.edge_index is None:
                 raise RuntimeError("CSRGraph: transposed CSR was not pre-built and edge_index is gone")
-            rp, col, _, _, st = csr_build_raw(self.edge_index, self.num_nodes, by_src=True, want_perm=False, want_inv_deg=False)
-            self.rowptr_t, self.col_t = rp, col
+            self.rowptr_t, self.col_t, self.status_t = csr_transpose_raw(self.edge_index, self.num_nodes, self.rowptr, self.col)
         return self.rowptr_t, self.col_t
 
     def check(self) -> None:
@@ -168,6 +168,23 @@ def csr_build_raw(edge_index: torch.Tensor, num_nodes: int, by_src: bool = False
                                 status.data_ptr(), ws.data_ptr(), ws_bytes, _stream(ei)))
     LAUNCH_COUNTER["kernels"] += 7 if E > 0 else 3
     return rowptr, col, perm, inv_deg, status
+
+
+def csr_transpose_raw(edge_index: torch.Tensor, num_nodes: int, rowptr: torch.Tensor, col: torch.Tensor):
+    """CSR by source for the backward gather (``dfw_csr_transpose``): a copy of the CSR by destination when the graph
+    holds both directions of every edge (checked on the device), the general build otherwise."""
+    ei = edge_index.contiguous()
+    E, N, dev = int(ei.shape[1]), int(num_nodes), ei.device
+    rowptr_t = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    col_t = torch.empty(E, dtype=torch.int32, device=dev)
+    status = torch.empty(3, dtype=torch.int32, device=dev)
+    ws_bytes = lib.dfw_csr_ws_bytes(E, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev), _prof("csr_transpose", 16 * E + 4 * E + 4 * (N + 1)):
+        check(lib.dfw_csr_transpose(ei.data_ptr(), E, N, rowptr.data_ptr(), _ptr(col), rowptr_t.data_ptr(), _ptr(col_t),
+                                    status.data_ptr(), ws.data_ptr(), ws_bytes, _stream(ei)))
+    LAUNCH_COUNTER["kernels"] += 9 if E > 0 else 5
+    return rowptr_t, col_t, status
 
 
 def faces_to_graph(faces: torch.Tensor, num_nodes: int, node_ids: torch.Tensor | None = None, want_edge_index: bool = True):

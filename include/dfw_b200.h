@@ -64,6 +64,14 @@ size_t dfw_csr_ws_bytes(int64_t E, int64_t N);
 int dfw_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src,
                   int32_t* rowptr, int32_t* col, int32_t* perm, float* inv_deg,
                   int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
+/*     Transposed CSR (rows = source) for the backward gather, given the CSR by destination that dfw_csr_build made of
+ *     the same edge_index.  Mesh graphs hold both directions of every edge (dataset.py:55-58); the call verifies that
+ *     on the device (duplicate-free rows and a mirror for every edge) and then COPIES the CSR instead of building one;
+ *     otherwise it runs the general build (by_src = 1).  No host synchronisation either way (capturable).
+ *     status int32 [3]: [0], [1] as above for the general build, [2] = 1 when the graph was NOT symmetric.
+ *     ws: dfw_csr_ws_bytes(E, N). */
+int dfw_csr_transpose(const int64_t* edge_index, int64_t E, int64_t N, const int32_t* rowptr, const int32_t* col,
+                      int32_t* rowptr_t, int32_t* col_t, int32_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (f1) graph construction from triangle faces: _faces_to_edge_index (dataset.py:26-63) on the device.

@@ -81,6 +81,29 @@ def test_csr_input_order_invariance(ops):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])  # canonical whatever the edge order
 
 
+def test_csr_transpose_copies_symmetric_graphs_and_builds_the_rest(ops):
+    """``dfw_csr_transpose`` == the by-source CSR of the oracle, bit-exact, whether the device-side symmetry check takes
+    the copy path (mesh graphs, self loops) or the general build (one-directional edges, duplicate edges)."""
+    from deep_fem_uav_wing.gnn import synth
+
+    rng = np.random.default_rng(5)
+    mesh = synth.surface_tri_wing(3000, seed=3)
+    tet = synth.tet_lattice_wing(2000, seed=4)
+    sym_loops = np.array([[0, 1, 1, 2, 2, 0, 3], [1, 0, 2, 1, 0, 2, 3]], dtype=np.int64)  # triangle + a self loop
+    one_way = np.array([[0, 1, 2], [1, 2, 0]], dtype=np.int64)
+    dup_sym = np.array([[0, 1, 0, 1], [1, 0, 1, 0]], dtype=np.int64)  # symmetric as a multigraph: general path
+    cases = [(mesh["edge_index"], mesh["num_nodes"], 0), (tet["edge_index"], tet["num_nodes"], 0), (sym_loops, 5, 0),
+             (one_way, 3, 1), (dup_sym, 2, 1), (rng.integers(0, 500, size=(2, 6000)).astype(np.int64), 500, 1),
+             (np.zeros((2, 0), dtype=np.int64), 7, 0)]
+    for ei_np, n, asym in cases:
+        ei = torch.from_numpy(np.ascontiguousarray(ei_np)).cuda()
+        rowptr, col, _, _, _ = ops.csr_build_raw(ei, n, by_src=False, want_perm=False)
+        rp_t, col_t, status = ops.csr_transpose_raw(ei, n, rowptr, col)
+        o = csr_oracle_c(ei_np, n, "src")
+        assert int(status[2]) == asym
+        assert torch.equal(rp_t.cpu(), torch.from_numpy(o[0])) and torch.equal(col_t.cpu(), torch.from_numpy(o[1]))
+
+
 @pytest.mark.parametrize("h", [4, 16, 64, 128, 256, 96])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_aggregate_matches_oracle(ops, h, dtype):
