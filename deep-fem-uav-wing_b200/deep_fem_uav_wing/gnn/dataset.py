@@ -22,6 +22,7 @@ from typing import Any
 import numpy as np
 import torch
 
+from .caseio import load_packed_case, packed_path, read_case
 from .loader import Data
 
 
@@ -68,16 +69,23 @@ def build_graph_data(surface_npz_path: Path, boundary_sets_path: Path, params_pa
     ``edge_index [2,E] i64``, ``y [N,1] f32`` (= log1p(stress) by default), ``loss_mask [N] bool``,
     ``pos``, ``disp``, ``stress_vm_raw``, ``case_id``, ``global_params``, ``global_params_raw``.
     """
-    npz = np.load(surface_npz_path)
-    boundary_sets = json.loads(Path(boundary_sets_path).read_text(encoding="utf-8"))
-    params = json.loads(Path(params_path).read_text(encoding="utf-8"))
+    return _graph_from_raw(read_case(surface_npz_path, boundary_sets_path, params_path), log_scale_stress, normalize_pos)
 
-    node_ids = npz["node_id"]
-    pos = npz["pos"].astype(np.float32)
-    normal = npz["normal"].astype(np.float32)
-    stress_vm = npz["stress_vm"].astype(np.float32)
-    disp = npz["disp"].astype(np.float32)
-    loss_mask = npz["loss_mask"].astype(bool)
+
+def build_graph_data_packed(packed_npz_path: Path, *, log_scale_stress: bool = True, normalize_pos: bool = True) -> dict[str, Any]:
+    """:func:`build_graph_data` from the single-file case format of ``gnn/caseio.py``: same result,
+    bit for bit, without parsing the JSON face list."""
+    return _graph_from_raw(load_packed_case(packed_npz_path), log_scale_stress, normalize_pos)
+
+
+def _graph_from_raw(raw: dict, log_scale_stress: bool, normalize_pos: bool) -> dict[str, Any]:
+    params = {**raw["params"], "case_id": raw["case_id"]}
+    node_ids = raw["node_id"]
+    pos = raw["pos"].astype(np.float32)
+    normal = raw["normal"].astype(np.float32)
+    stress_vm = raw["stress_vm"].astype(np.float32)
+    disp = raw["disp"].astype(np.float32)
+    loss_mask = raw["loss_mask"].astype(bool)
     n = len(node_ids)
 
     ids = np.asarray(node_ids, dtype=np.int64)
@@ -87,7 +95,7 @@ def build_graph_data(surface_npz_path: Path, boundary_sets_path: Path, params_pa
     if n > 1 and np.any(sorted_ids[1:] == sorted_ids[:-1]):
         keep = np.append(sorted_ids[1:] != sorted_ids[:-1], True)
         sorted_ids, sorted_idx = sorted_ids[keep], sorted_idx[keep]
-    edge_index = _faces_to_edge_index(boundary_sets["surf_all_faces"], (sorted_ids, sorted_idx))
+    edge_index = _faces_to_edge_index(raw["faces"], (sorted_ids, sorted_idx))
 
     span_m, chord_m = params["span_m"], params["chord_m"]
     sweep_deg, thickness_ratio = params["sweep_deg"], params["thickness_ratio"]
@@ -136,23 +144,37 @@ def build_graph_data_device(surface_npz_path: Path, boundary_sets_path: Path, pa
     rebuild it), the rest stays numpy.  The host only parses the three files and copies the RAW arrays:
     ``dfw_faces_to_csr`` replaces the Python set loop of ``_faces_to_edge_index`` (``dataset.py:26-63``) and
     ``dfw_node_features`` the numpy block of ``dataset.py:129-151``."""
+    return _graph_from_raw_device(read_case(surface_npz_path, boundary_sets_path, params_path), device, log_scale_stress,
+                                  normalize_pos)
+
+
+def build_graph_data_device_packed(packed_npz_path: Path, *, device="cuda", log_scale_stress: bool = True,
+                                   normalize_pos: bool = True) -> dict[str, Any]:
+    """:func:`build_graph_data_device` from the single-file case format (``gnn/caseio.py``): no JSON on the way to the GPU."""
+    return _graph_from_raw_device(load_packed_case(packed_npz_path), device, log_scale_stress, normalize_pos)
+
+
+def graph_from_raw_device(raw: dict, *, device="cuda", log_scale_stress: bool = True, normalize_pos: bool = True) -> dict[str, Any]:
+    """Device-side graph build from the raw arrays of ``caseio.read_case`` / ``caseio.load_packed_case`` (a caller that
+    also needs the faces, e.g. for the GLB export, reads the case once)."""
+    return _graph_from_raw_device(raw, device, log_scale_stress, normalize_pos)
+
+
+def _graph_from_raw_device(raw: dict, device, log_scale_stress: bool, normalize_pos: bool) -> dict[str, Any]:
     from . import ops
 
     dev = torch.device(device)
-    npz = np.load(surface_npz_path)
-    boundary_sets = json.loads(Path(boundary_sets_path).read_text(encoding="utf-8"))
-    params = json.loads(Path(params_path).read_text(encoding="utf-8"))
+    npz, params = raw, {**raw["params"], "case_id": raw["case_id"]}
     node_ids = np.asarray(npz["node_id"], dtype=np.int64)
     n = len(node_ids)
     if n > 1 and np.unique(node_ids).size != n:  # duplicate ids (last one wins in the reference's dict): host path
-        g = build_graph_data(surface_npz_path, boundary_sets_path, params_path, log_scale_stress=log_scale_stress,
-                             normalize_pos=normalize_pos)
+        g = _graph_from_raw(raw, log_scale_stress, normalize_pos)
         for k in ("x", "edge_index", "y", "loss_mask", "pos"):
             g[k] = torch.from_numpy(np.asarray(g[k])).to(dev)
         return g
     pos = npz["pos"].astype(np.float32)
     stress_vm = npz["stress_vm"].astype(np.float32)
-    faces = np.asarray(boundary_sets["surf_all_faces"], dtype=np.int64).reshape(-1, 3)
+    faces = np.ascontiguousarray(raw["faces"], dtype=np.int64).reshape(-1, 3)
     span_m, chord_m = params["span_m"], params["chord_m"]
     sweep_deg, thickness_ratio = params["sweep_deg"], params["thickness_ratio"]
     global_params = np.array(
@@ -257,9 +279,12 @@ class WingStressDataset:
         data_list = []
         for cid in case_ids:
             try:
-                g = build_graph_data(fem_dir / cid / "surface_results.npz", mesh_dir / cid / "boundary_sets.json",
-                                     geometry_dir / cid / "params.json", log_scale_stress=self.log_scale_stress,
-                                     normalize_pos=self.normalize_pos)
+                src = (fem_dir / cid / "surface_results.npz", mesh_dir / cid / "boundary_sets.json", geometry_dir / cid / "params.json")
+                packed = packed_path(self.root, cid)  # single-file cache of the case (gnn/caseio.py), if it is up to date
+                if packed.exists() and packed.stat().st_mtime >= max(q.stat().st_mtime for q in src):
+                    g = build_graph_data_packed(packed, log_scale_stress=self.log_scale_stress, normalize_pos=self.normalize_pos)
+                else:
+                    g = build_graph_data(*src, log_scale_stress=self.log_scale_stress, normalize_pos=self.normalize_pos)
                 d = graph_dict_to_data(g)
                 if self.pre_transform is not None:
                     d = self.pre_transform(d)

@@ -20,7 +20,8 @@ sys.path.insert(0, str(PKG_ROOT))
 
 import torch  # noqa: E402
 
-from deep_fem_uav_wing.gnn.dataset import build_graph_data, build_graph_data_device  # noqa: E402
+from deep_fem_uav_wing.gnn import caseio  # noqa: E402
+from deep_fem_uav_wing.gnn.dataset import build_graph_data, build_graph_data_device, graph_from_raw_device  # noqa: E402
 from deep_fem_uav_wing.gnn.glb import hot_rgb, viridis_rgb, write_glb  # noqa: E402
 from deep_fem_uav_wing.gnn.model import GraphSAGEModel, compute_metrics  # noqa: E402
 
@@ -35,23 +36,31 @@ def load_model(checkpoint_path: Path, device: torch.device) -> GraphSAGEModel:
     return model
 
 
-def _surface_faces(npz, boundary_sets) -> np.ndarray:
-    ids = np.asarray(npz["node_id"], dtype=np.int64)
+def _surface_faces(node_id, faces) -> np.ndarray:
+    ids = np.asarray(node_id, dtype=np.int64)
     order = np.argsort(ids, kind="stable")
-    f = np.asarray(boundary_sets["surf_all_faces"], dtype=np.int64).reshape(-1, 3)
+    f = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
     pos = np.minimum(np.searchsorted(ids[order], f), len(ids) - 1)
     ok = (ids[order][pos] == f).all(axis=1)
     return order[pos][ok].astype(np.uint32)
 
 
-def run_inference(model, case_id: str, device, paths: dict, *, log_scale_stress: bool = True, deform_scale: float = 10.0) -> dict:
+def run_inference(model, case_id: str, device, paths: dict, *, log_scale_stress: bool = True, deform_scale: float = 10.0,
+                  writer=None) -> dict:
     fem_dir, mesh_dir, geometry_dir = paths["fem_dir"], paths["mesh_dir"], paths["geometry_dir"]
     npz_p, bs_p, par_p = fem_dir / case_id / "surface_results.npz", mesh_dir / case_id / "boundary_sets.json", geometry_dir / case_id / "params.json"
     for q, name in ((npz_p, "surface_results.npz"), (bs_p, "boundary_sets.json"), (par_p, "params.json")):
         if not q.exists():
             return {"status": "failed", "reason": f"{name} not found"}
-    # graph construction (faces -> CSR) and feature assembly run on the GPU (dfw_faces_to_csr, dfw_node_features)
-    g = build_graph_data_device(npz_p, bs_p, par_p, device=device, log_scale_stress=log_scale_stress, normalize_pos=True)
+    # the case is read ONCE: from its single-file cache when that is up to date (gnn/caseio.py: no JSON face list to parse),
+    # else from the reference's three files; graph construction (faces -> CSR) and feature assembly run on the GPU
+    # (dfw_faces_to_csr, dfw_node_features)
+    packed = paths.get("packed_dir") and paths["packed_dir"] / f"{case_id}.npz"
+    if packed and packed.exists() and packed.stat().st_mtime >= max(q.stat().st_mtime for q in (npz_p, bs_p, par_p)):
+        raw = caseio.load_packed_case(packed)
+    else:
+        raw = caseio.read_case(npz_p, bs_p, par_p)
+    g = graph_from_raw_device(raw, device=device, log_scale_stress=log_scale_stress, normalize_pos=True)
     x, edge_index, y, loss_mask = g["x"], g["edge_index"], g["y"], g["loss_mask"]
     g["loss_mask"] = loss_mask.cpu().numpy()
     with torch.no_grad():
@@ -62,8 +71,8 @@ def run_inference(model, case_id: str, device, paths: dict, *, log_scale_stress:
     gt = g["stress_vm_raw"]
     error = np.abs(gt - pred_stress)
 
-    npz = np.load(npz_p)
-    faces = _surface_faces(npz, json.loads(bs_p.read_text(encoding="utf-8")))
+    npz = raw
+    faces = _surface_faces(raw["node_id"], raw["faces"])
     pred_glb, err_glb = fem_dir / case_id / "wing_pred.glb", fem_dir / case_id / "wing_error.glb"
     ok = len(faces) > 0
     if ok:
@@ -81,7 +90,10 @@ def run_inference(model, case_id: str, device, paths: dict, *, log_scale_stress:
         "pred_stress_range": [float(pred_stress.min()), float(pred_stress.max())],
         "gt_stress_range": [float(gt.min()), float(gt.max())], "error_range": [float(error.min()), float(error.max())],
     }
-    (fem_dir / case_id / "inference_report.json").write_text(json.dumps(report, indent=2), encoding="utf-8")
+    if writer is not None:
+        writer.add(report)  # written in one go at the end of the run (caseio.ReportWriter)
+    else:
+        (fem_dir / case_id / "inference_report.json").write_text(json.dumps(report, indent=2), encoding="utf-8")
     return report
 
 
@@ -94,6 +106,7 @@ def main():
     p.add_argument("--device", type=str, default="auto")
     p.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32")
     p.add_argument("--root", type=str, default=os.environ.get("DFW_PROJECT_ROOT", str(Path.cwd())))
+    p.add_argument("--pack", action="store_true", help="write/refresh the single-file case caches under data/packed first (gnn/caseio.py)")
     args = p.parse_args()
     if not args.case_id and not args.all:
         p.error("give --case-id or --all")
@@ -104,21 +117,25 @@ def main():
     torch.cuda.set_device(device)
     root = Path(args.root)
     raw = root / "data" / "raw"
-    paths = {"fem_dir": raw / "fem", "mesh_dir": raw / "mesh", "geometry_dir": raw / "geometry"}
+    paths = {"fem_dir": raw / "fem", "mesh_dir": raw / "mesh", "geometry_dir": raw / "geometry", "packed_dir": root / "data" / "packed"}
+    if args.pack and rank == 0:
+        print(f"[Inference] packed {len(caseio.pack_dataset(root))} case(s) under {paths['packed_dir']}")
     model = load_model(root / args.checkpoint, device)
     if args.dtype == "bf16":
         model.set_compute_dtype(torch.bfloat16)
     case_ids = [args.case_id] if args.case_id else sorted(d.name for d in paths["fem_dir"].iterdir() if d.is_dir())
     mine = case_ids[rank::world]
     results = []
+    writer = caseio.ReportWriter(paths["fem_dir"])
     for cid in mine:
-        r = run_inference(model, cid, device, paths, deform_scale=args.deform_scale)
+        r = run_inference(model, cid, device, paths, deform_scale=args.deform_scale, writer=writer)
         results.append(r)
         if r.get("status") in ("success", "partial"):
             mm = r["metrics"]["masked_nodes"]
             print(f"[Inference] {cid}: masked MAE {mm['mae']:.2e} Pa, RMSE {mm['rmse']:.2e} Pa")
         else:
             print(f"[Inference] {cid}: {r.get('status')} ({r.get('reason')})")
+    writer.flush()
     good = [r for r in results if r.get("status") in ("success", "partial")]
     print(f"\n[Inference] Completed: {len(good)}/{len(results)} successful")
     if world == 1:  # same schema as the reference (inference_gnn.py:416-423)
