@@ -62,3 +62,11 @@ def test_train_then_inference_scripts_end_to_end(tmp_path):
     rep = json.loads((case / "inference_report.json").read_text())
     assert rep["status"] == "success" and {"all_nodes", "masked_nodes"} == set(rep["metrics"])
     assert (case / "wing_pred.glb").read_bytes()[:4] == b"glTF" and (case / "wing_error.glb").exists()
+    # the same run from the single-file case caches (gnn/caseio.py): identical reports, byte for byte
+    reports = {c.name: (c / "inference_report.json").read_text() for c in (tmp_path / "data" / "raw" / "fem").iterdir()}
+    r = subprocess.run([sys.executable, str(PKG / "scripts" / "inference_gnn.py"), "--root", str(tmp_path), "--all", "--pack", "--checkpoint",
+                        "checkpoints/final_model.pt"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "packed 10 case(s)" in r.stdout and len(list((tmp_path / "data" / "packed").glob("*.npz"))) == 10
+    for name, text in reports.items():
+        assert (tmp_path / "data" / "raw" / "fem" / name / "inference_report.json").read_text() == text, name
