@@ -71,8 +71,17 @@ def cfg1():
             out = model(xd, eid)
             err = ((out.cpu() - out_ref).abs().max() / out_ref.abs().max()).item()
             med, p10, p90 = gpu_time(lambda: model(xd, eid), flush=False)
+            # the same forward replayed from a CUDA graph (gnn/graphed.py): a 20k-node mesh is launch-bound when its ~20
+            # kernels are issued one by one from Python
+            from deep_fem_uav_wing.gnn.graphed import GraphedForward
+
+            gf = GraphedForward(model)
+            out_g = gf(xd, eid)
+            assert torch.equal(out_g, out)
+            gmed, _, _ = gpu_time(lambda: gf(xd, eid), flush=False)
         print(json.dumps({"config": f"cfg1-{kind}", "N": mesh["num_nodes"], "E": int(ei.shape[1]), "hidden": 64, "layers": 3, "dtype": "f32",
                           "gpu_forward_us": round(med * 1e6, 1), "gpu_p10_us": round(p10 * 1e6, 1), "gpu_p90_us": round(p90 * 1e6, 1),
+                          "gpu_forward_cuda_graph_us": round(gmed * 1e6, 1),
                           "gpu_nodes_per_s": mesh["num_nodes"] / med, "cpu_forward_ms": round(cpu_s * 1e3, 2), "cpu_threads": torch.get_num_threads(),
                           "speedup_vs_cpu_oracle": cpu_s / med, "fwd_rel_err_vs_oracle": err, "note": "CSR cached (one-time build); L2-resident mesh"}), flush=True)
 
