@@ -127,9 +127,13 @@ class GraphedForward:
         if entry is None:
             if len(self._graphs) >= self.max_graphs:
                 return self.model(x, edge_index)
+            # warm-up (lazy initialisation outside the capture) on the CALLER's tensors: the static edge_index buffer must
+            # reach the capture without a cached CSR, so that the CSR build is part of the graph and every replay rebuilds
+            # it from the edge_index of that call (a CSR cached for the buffer would be silently reused for every later
+            # graph of the same shape)
+            self.model(x, edge_index)
             sx, se = torch.empty_like(x), torch.empty_like(edge_index)
             sx.copy_(x); se.copy_(edge_index)
-            self.model(sx, se)  # warm-up (lazy initialisation outside the capture)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

@@ -289,6 +289,14 @@ def test_cuda_graph_training_step_matches_eager():
     with torch.no_grad():
         for x, ei, _, _ in batches[:3]:
             assert rel_max(gf(x, ei), model(x, ei)) < TOL_FP32
+        # a DIFFERENT graph of the SAME shape replays the same CUDA graph: its CSR must be rebuilt inside the replay
+        x, ei, _, _ = batches[0]
+        perm = torch.randperm(x.shape[0], device=x.device)
+        ei2 = perm[ei]  # relabelled nodes: same [2, E] shape, different edges
+        assert not torch.equal(ei2, ei)
+        for _ in range(2):
+            assert rel_max(gf(x, ei2), model(x, ei2)) < TOL_FP32
+            assert rel_max(gf(x, ei), model(x, ei)) < TOL_FP32
 
 
 @pytest.mark.gpu
