@@ -1,0 +1,114 @@
+// One-call SAGE layer (dfw_sage_layer_fwd / dfw_sage_layer_bwd): the launch sequences that
+// gnn/ops.py:SageConvFn issues piece by piece, behind one C entry point each, for hosts that drive a whole layer of
+//     h' = h + dropout(relu(LayerNorm(lin_l(mean_j h_j) + lin_r(h))))          (reference model.py:90-95)
+// without a Python autograd tape.  Host code only: every kernel belongs to the entry points it calls, so the results
+// are bit-identical to the piecewise path (tests/test_gpu_kernels.py).  Workspace carve-up (all 256-byte aligned):
+//   fwd: [linear]                                   bwd: [g_y | g_t | epilogue | weight-gradient | linear]
+#include <algorithm>
+
+#include "dfw_common.cuh"
+
+namespace dfw {
+namespace {
+struct BwdWs {
+    size_t o_gy, o_gt, o_epi, o_dw, o_lin, epi_bytes, dw_bytes, lin_bytes, total;
+};
+BwdWs carve_bwd(int64_t N, int64_t Hin, int64_t Hout, int dtype, bool want_gx) {
+    const size_t e = dtype == DFW_F32 ? 4 : 2;
+    BwdWs w{};
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+    w.o_gy = take((size_t)N * Hout * e);
+    w.o_gt = take(want_gx ? (size_t)N * Hout * e : 0);
+    w.epi_bytes = dfw_epilogue_bwd_ws_bytes(N, Hout);
+    w.o_epi = take(w.epi_bytes);
+    w.dw_bytes = dfw_linear_bwd_weight_ws_bytes(N, Hout, Hin, Hin);
+    w.o_dw = take(w.dw_bytes);
+    w.lin_bytes = want_gx ? dfw_linear_ws_bytes(Hin, Hout, Hout, dtype) : 0;
+    w.o_lin = take(w.lin_bytes);
+    w.total = off + 256;
+    return w;
+}
+inline char* base256(void* ws) { return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255)); }
+}  // namespace
+}  // namespace dfw
+
+extern "C" size_t dfw_sage_layer_fwd_ws_bytes(int64_t N, int64_t Hin, int64_t Hout, int dtype) {
+    if (N < 0 || Hin < 1 || Hout < 1) return 0;
+    return dfw_linear_ws_bytes(Hout, Hin, Hin, dtype);
+}
+
+extern "C" int dfw_sage_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* inv_deg, const void* x, const void* w_l,
+                                  const float* b_l, const void* w_r, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                  float dropout_p, uint64_t seed, int flags, void* agg, void* pre_out, float* ln_stats, void* out,
+                                  int64_t N, int64_t E, int64_t Hin, int64_t Hout, int dtype, void* ws, size_t ws_bytes,
+                                  dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(x && w_l && w_r && agg && out, "dfw_sage_layer_fwd: null pointer");
+    DFW_REQUIRE(!(flags & DFW_EP_RESIDUAL) || Hin == Hout, "dfw_sage_layer_fwd: the residual h + h_new needs Hin == Hout (%lld, %lld)",
+                (long long)Hin, (long long)Hout);
+    DFW_REQUIRE(!(flags & DFW_EP_TRANSPOSE_W), "dfw_sage_layer_fwd: weights are [Hout, Hin]");
+    int rc = dfw_sage_aggregate(rowptr, col, inv_deg, x, nullptr, agg, N, E, Hin, dtype, stream);
+    if (rc) return rc;
+    return dfw_linear_fwd(agg, w_l, Hin, x, w_r, Hin, b_l, ln_gamma, ln_beta, ln_eps, (flags & DFW_EP_RESIDUAL) ? x : nullptr, dropout_p,
+                          seed, out, pre_out, ln_stats, nullptr, nullptr, nullptr, N, Hout, flags, dtype, ws, ws_bytes, stream);
+}
+
+extern "C" size_t dfw_sage_layer_bwd_ws_bytes(int64_t N, int64_t Hin, int64_t Hout, int dtype, int want_input_grad) {
+    if (N < 0 || Hin < 1 || Hout < 1) return 0;
+    return dfw::carve_bwd(N, Hin, Hout, dtype, want_input_grad != 0).total;
+}
+
+extern "C" int dfw_sage_layer_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg, const void* x, const void* agg,
+                                  const void* pre_out, const float* ln_stats, const void* w_l, const void* w_r, const float* ln_gamma,
+                                  const float* ln_beta, const void* g_out, float dropout_p, uint64_t seed, int flags, void* g_x,
+                                  float* dw_l, float* db_l, float* dw_r, float* dgamma, float* dbeta, int64_t N, int64_t E, int64_t Hin,
+                                  int64_t Hout, int dtype, void* ws, size_t ws_bytes, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(x && agg && g_out && dw_l && dw_r, "dfw_sage_layer_bwd: null pointer");
+    DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_sage_layer_bwd: unknown dtype %d", dtype);
+    const bool tail = flags & DFW_EP_LAYERNORM;  // the fused LayerNorm -> ReLU -> dropout -> residual tail of model.py:91-95
+    DFW_REQUIRE(!tail || (pre_out && ln_stats && ln_gamma && ln_beta && dgamma && dbeta),
+                "dfw_sage_layer_bwd: the LayerNorm tail needs pre_out, ln_stats, gamma/beta and dgamma/dbeta");
+    DFW_REQUIRE(tail || !(flags & (DFW_EP_RELU | DFW_EP_DROPOUT | DFW_EP_RESIDUAL)),
+                "dfw_sage_layer_bwd: ReLU / dropout / residual without LayerNorm is not a layer of this model");
+    DFW_REQUIRE(!g_x || (w_l && w_r && rowptr_t && (col_t || E == 0) && inv_deg), "dfw_sage_layer_bwd: the input gradient needs the weights and the transposed CSR");
+    const BwdWs w = carve_bwd(N, Hin, Hout, dtype, g_x != nullptr);
+    DFW_REQUIRE(ws && ws_bytes >= w.total, "dfw_sage_layer_bwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    if (N == 0) {  // nothing flows: the parameter gradients of an empty batch are zero
+        cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+        DFW_CUDA(cudaMemsetAsync(dw_l, 0, sizeof(float) * (size_t)Hout * Hin, s));
+        DFW_CUDA(cudaMemsetAsync(dw_r, 0, sizeof(float) * (size_t)Hout * Hin, s));
+        if (db_l) DFW_CUDA(cudaMemsetAsync(db_l, 0, sizeof(float) * (size_t)Hout, s));
+        if (dgamma) DFW_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * (size_t)Hout, s));
+        if (dbeta) DFW_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * (size_t)Hout, s));
+        return 0;
+    }
+    char* base = base256(ws);
+    const void* g_y = g_out;
+    int rc;
+    if (tail) {
+        // g_y = dL/d(lin_l + lin_r): LayerNorm / ReLU / dropout backward, plus the column sums of g_y = lin_l's bias gradient
+        void* gy = base + w.o_gy;
+        rc = dfw_epilogue_bwd(g_out, nullptr, nullptr, pre_out, ln_stats, nullptr, ln_gamma, ln_beta, dropout_p, seed, gy, dgamma, dbeta,
+                              nullptr, nullptr, db_l, N, Hout, flags & (DFW_EP_RELU | DFW_EP_LAYERNORM | DFW_EP_DROPOUT | DFW_EP_SEED_IS_PTR),
+                              dtype, base + w.o_epi, w.epi_bytes, stream);
+        if (rc) return rc;
+        g_y = gy;
+    }
+    // dW_l = g_y^T agg, dW_r = g_y^T x (and db_l when there is no tail to emit it)
+    rc = dfw_linear_bwd_weight(g_y, agg, Hin, x, Hin, dw_l, dw_r, tail ? nullptr : db_l, N, Hout, dtype, 0, base + w.o_dw, w.dw_bytes, stream);
+    if (rc) return rc;
+    if (!g_x) return 0;
+    // dL/dx = (A^T D^-1 g_y) W_l + g_y W_r (+ g_out through the residual): aggregate the gradient first, then ONE two-operand
+    // contraction on the forward's weights (DFW_EP_TRANSPOSE_W)
+    DFW_REQUIRE(dfw_linear_tc_eligible(N, Hin, Hout, Hout, dtype), "dfw_sage_layer_bwd: (Hin=%lld, Hout=%lld) is outside the tensor-core "
+                "path; use dfw_linear_bwd_input + dfw_sage_aggregate for this shape", (long long)Hin, (long long)Hout);
+    void* g_t = base + w.o_gt;
+    rc = dfw_sage_aggregate_scaled(rowptr_t, col_t, inv_deg, g_y, g_t, N, E, Hout, dtype, stream);
+    if (rc) return rc;
+    const bool res = tail && (flags & DFW_EP_RESIDUAL);
+    return dfw_linear_fwd(g_t, w_l, Hout, g_y, w_r, Hout, nullptr, nullptr, nullptr, 0.f, res ? g_out : nullptr, 0.f, 0, g_x, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, N, Hin, DFW_EP_TRANSPOSE_W | (res ? DFW_EP_RESIDUAL : 0), dtype, base + w.o_lin, w.lin_bytes,
+                          stream);
+}

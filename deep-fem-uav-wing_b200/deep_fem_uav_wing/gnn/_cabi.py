@@ -48,6 +48,14 @@ SIGNATURES = {
     "dfw_linear_bwd_weight_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "dfw_linear_bwd_weight": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "dfw_sage_layer_fwd_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "dfw_sage_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_float, c_float, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "dfw_sage_layer_bwd_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
+    "dfw_sage_layer_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "dfw_masked_mse_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "dfw_masked_mse_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),

@@ -506,6 +506,63 @@ def _grad_to(param: torch.Tensor, g):
     return g if g.dtype == param.dtype else g.to(param.dtype)
 
 
+def sage_layer_fwd(graph: "CSRGraph", x, w_l, b_l, w_r, ln=None, eps=1e-5, dropout_p=0.0, seed=0, residual=True, save=True):
+    """One-call SAGE layer forward (``dfw_sage_layer_fwd``): ``h + dropout(relu(LayerNorm(lin_l(mean) + lin_r(h))))`` with
+    ``ln = (gamma, beta)``, or the bare ``SAGEConv`` with ``ln = None``.  Returns ``(out, agg, pre, stats)``."""
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    N, Hin = x.shape
+    Hout = w_l.shape[0]
+    dev, dt = x.device, x.dtype
+    seed_v, seed_flag = _seed_arg(seed)
+    flags = 0
+    if ln is not None:
+        flags |= EP_LAYERNORM | EP_RELU | (EP_RESIDUAL if residual else 0) | ((EP_DROPOUT | seed_flag) if dropout_p > 0.0 else 0)
+    agg = torch.empty_like(x)
+    out = torch.empty(N, Hout, dtype=dt, device=dev)
+    pre = torch.empty(N, Hout, dtype=dt, device=dev) if (save and ln is not None) else None
+    stats = torch.empty(N, 2, dtype=torch.float32, device=dev) if (save and ln is not None) else None
+    ws_bytes = lib.dfw_sage_layer_fwd_ws_bytes(N, Hin, Hout, _dt(x))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dfw_sage_layer_fwd(graph.rowptr.data_ptr(), graph.col.data_ptr(), graph.inv_deg.data_ptr(), x.data_ptr(),
+                                     w_l.data_ptr(), _ptr(b_l), w_r.data_ptr(), _ptr(ln[0]) if ln else None, _ptr(ln[1]) if ln else None,
+                                     float(eps), float(dropout_p), seed_v, flags, agg.data_ptr(), _ptr(pre), _ptr(stats), out.data_ptr(),
+                                     N, graph.num_edges, Hin, Hout, _dt(x), ws.data_ptr(), ws_bytes, _stream(x)))
+    LAUNCH_COUNTER["kernels"] += 2
+    return out, agg, pre, stats
+
+
+def sage_layer_bwd(graph: "CSRGraph", x, agg, pre, stats, w_l, w_r, ln, g_out, dropout_p=0.0, seed=0, residual=True,
+                   want_input_grad=True, has_bias=True):
+    """One-call SAGE layer backward (``dfw_sage_layer_bwd``).  Returns ``(g_x, dw_l, db_l, dw_r, dgamma, dbeta)``."""
+    g_out = g_out.contiguous()
+    N, Hout = g_out.shape
+    Hin = x.shape[1]
+    dev = x.device
+    seed_v, seed_flag = _seed_arg(seed)
+    flags = 0
+    if ln is not None:
+        flags |= EP_LAYERNORM | EP_RELU | (EP_RESIDUAL if residual else 0) | ((EP_DROPOUT | seed_flag) if dropout_p > 0.0 else 0)
+    f32 = dict(dtype=torch.float32, device=dev)
+    g_x = torch.empty(N, Hin, dtype=x.dtype, device=dev) if want_input_grad else None
+    dw_l, dw_r = torch.empty(Hout, Hin, **f32), torch.empty(Hout, Hin, **f32)
+    db_l = torch.empty(Hout, **f32) if has_bias else None
+    dgamma = torch.empty(Hout, **f32) if ln is not None else None
+    dbeta = torch.empty(Hout, **f32) if ln is not None else None
+    rp_t, col_t = graph.transpose() if want_input_grad else (None, None)
+    ws_bytes = lib.dfw_sage_layer_bwd_ws_bytes(N, Hin, Hout, _dt(x), int(want_input_grad))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dfw_sage_layer_bwd(_ptr(rp_t), _ptr(col_t), graph.inv_deg.data_ptr(), x.data_ptr(), agg.data_ptr(), _ptr(pre), _ptr(stats),
+                                     w_l.data_ptr(), w_r.data_ptr(), _ptr(ln[0]) if ln else None, _ptr(ln[1]) if ln else None,
+                                     g_out.data_ptr(), float(dropout_p), seed_v, flags, _ptr(g_x), dw_l.data_ptr(), _ptr(db_l),
+                                     dw_r.data_ptr(), _ptr(dgamma), _ptr(dbeta), N, graph.num_edges, Hin, Hout, _dt(x),
+                                     ws.data_ptr(), ws_bytes, _stream(x)))
+    LAUNCH_COUNTER["kernels"] += 7 if want_input_grad else 4
+    return g_x, dw_l, db_l, dw_r, dgamma, dbeta
+
+
 # ----------------------------------------------------------------------------------------------
 # autograd Functions
 # ----------------------------------------------------------------------------------------------

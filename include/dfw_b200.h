@@ -191,6 +191,33 @@ int dfw_linear_bwd_weight(const void* g_y, const void* a1, int64_t k1, const voi
                           void* ws, size_t ws_bytes, dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (b+c) / (d) One-call SAGE layer - the launch sequences of the entry points above behind one call each,
+ *      for hosts that drive a whole layer of   h' = h + dropout(relu(LayerNorm(lin_l(mean_j h_j) + lin_r(h))))
+ *      (model.py:90-95) without a Python autograd tape.  Bit-identical to calling the pieces.
+ *   fwd: agg [N,Hin] (the mean aggregate, saved for the backward), pre_out / ln_stats (nullable, saved for the backward),
+ *        out [N,Hout].  flags: DFW_EP_LAYERNORM | DFW_EP_RELU | DFW_EP_DROPOUT [| DFW_EP_SEED_IS_PTR] | DFW_EP_RESIDUAL
+ *        (residual = x, needs Hin == Hout), or 0 for a bare SAGEConv.  w_l, w_r [Hout,Hin] in the compute dtype.
+ *   bwd: given g_out = dL/d out, the tensors the forward saved and the transposed CSR (dfw_csr_transpose):
+ *        dw_l, dw_r fp32 [Hout,Hin], db_l fp32 [Hout] (nullable), dgamma/dbeta fp32 [Hout] (LayerNorm tail),
+ *        g_x [N,Hin] (nullable: first layer).  flags as in the forward.  The input gradient takes the tensor-core
+ *        contraction on the forward's weights, so (Hin, Hout) must satisfy dfw_linear_tc_eligible(N, Hin, Hout, Hout).
+ * ---------------------------------------------------------------------------------------- */
+size_t dfw_sage_layer_fwd_ws_bytes(int64_t N, int64_t Hin, int64_t Hout, int dtype);
+int dfw_sage_layer_fwd(const int32_t* rowptr, const int32_t* col, const float* inv_deg, const void* x,
+                       const void* w_l, const float* b_l, const void* w_r,
+                       const float* ln_gamma, const float* ln_beta, float ln_eps, float dropout_p, uint64_t seed, int flags,
+                       void* agg, void* pre_out, float* ln_stats, void* out,
+                       int64_t N, int64_t E, int64_t Hin, int64_t Hout, int dtype,
+                       void* ws, size_t ws_bytes, dfw_stream_t stream);
+size_t dfw_sage_layer_bwd_ws_bytes(int64_t N, int64_t Hin, int64_t Hout, int dtype, int want_input_grad);
+int dfw_sage_layer_bwd(const int32_t* rowptr_t, const int32_t* col_t, const float* inv_deg, const void* x, const void* agg,
+                       const void* pre_out, const float* ln_stats, const void* w_l, const void* w_r,
+                       const float* ln_gamma, const float* ln_beta, const void* g_out, float dropout_p, uint64_t seed, int flags,
+                       void* g_x, float* dw_l, float* db_l, float* dw_r, float* dgamma, float* dbeta,
+                       int64_t N, int64_t E, int64_t Hin, int64_t Hout, int dtype,
+                       void* ws, size_t ws_bytes, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Masked MSE (model.py:126-153) without boolean indexing / host sync.
  *   result fp32 [2]: [0] = loss (mean: sum/max(count,1); sum: sum), [1] = number of selected
  *   elements.  mask uint8 [N] (nullable = all rows).  pred/target fp32 or bf16 [N,C].

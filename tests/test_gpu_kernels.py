@@ -270,6 +270,52 @@ def test_tiny_k_linear_forward_and_weight_gradient(ops, k, hout, n, dtype):
     assert torch.equal(dw, dw2)  # fixed tile -> block assignment, fixed-order reductions
 
 
+@pytest.mark.parametrize("dtype,h,p", [(torch.float32, 128, 0.1), (torch.float32, 64, 0.0), (torch.bfloat16, 128, 0.2)])
+def test_one_call_sage_layer_equals_the_piecewise_path(ops, dtype, h, p):
+    """``dfw_sage_layer_fwd`` / ``dfw_sage_layer_bwd`` launch the same kernels as the autograd Function that the
+    model uses: outputs and every gradient are bit-identical - with the fused LayerNorm tail and as a bare SAGEConv."""
+    from deep_fem_uav_wing.gnn import synth
+
+    torch.manual_seed(h)
+    m = synth.tet_lattice_wing(3000, seed=11)
+    n, dev = m["num_nodes"], "cuda"
+    ei = torch.from_numpy(m["edge_index"]).to(dev)
+    graph = ops.get_graph(ei, n)
+    x = torch.randn(n, h, device=dev).to(dtype).requires_grad_(True)
+    w_l = (torch.randn(h, h, device=dev) / h**0.5).requires_grad_(True)
+    w_r = (torch.randn(h, h, device=dev) / h**0.5).requires_grad_(True)
+    b_l = torch.randn(h, device=dev).requires_grad_(True)
+    gamma = (torch.rand(h, device=dev) + 0.5).requires_grad_(True)
+    beta = torch.randn(h, device=dev).requires_grad_(True)
+    g_out = torch.randn(n, h, device=dev).to(dtype)
+    seed = 1234567
+    wl_c, wr_c = w_l.detach().to(dtype), w_r.detach().to(dtype)
+    for tail in (True, False):
+        for t in (x, w_l, w_r, b_l, gamma, beta):
+            t.grad = None
+        # piecewise: the model's autograd Function (gnn/ops.py:SageConvFn)
+        ref = ops.SageConvFn.apply(x, w_l, b_l, w_r, gamma if tail else None, beta if tail else None, graph, 1e-5, p if tail else 0.0, seed, tail)
+        ref.backward(g_out)
+        # one call each way
+        ln = (gamma.detach(), beta.detach()) if tail else None
+        out, agg, pre, stats = ops.sage_layer_fwd(graph, x.detach(), wl_c, b_l.detach(), wr_c, ln=ln, dropout_p=p if tail else 0.0, seed=seed)
+        assert torch.equal(out, ref.detach())
+        g_x, dw_l, db_l, dw_r, dgamma, dbeta = ops.sage_layer_bwd(graph, x.detach(), agg, pre, stats, wl_c, wr_c, ln, g_out,
+                                                                 dropout_p=p if tail else 0.0, seed=seed)
+        assert torch.equal(g_x, x.grad) and torch.equal(dw_l, w_l.grad) and torch.equal(dw_r, w_r.grad) and torch.equal(db_l, b_l.grad)
+        if tail:
+            assert torch.equal(dgamma, gamma.grad) and torch.equal(dbeta, beta.grad)
+        # first layer of a network: no input gradient wanted
+        _, dw_l2, _, dw_r2, _, _ = ops.sage_layer_bwd(graph, x.detach(), agg, pre, stats, wl_c, wr_c, ln, g_out, dropout_p=p if tail else 0.0,
+                                                      seed=seed, want_input_grad=False)
+        assert torch.equal(dw_l2, dw_l) and torch.equal(dw_r2, dw_r)
+    with pytest.raises(RuntimeError, match="tensor-core"):  # (24, 24) is not a tensor-core shape: the composite says so
+        xs = torch.randn(n, 24, device=dev)
+        ws_ = torch.randn(24, 24, device=dev)
+        o, a, _, _ = ops.sage_layer_fwd(graph, xs, ws_, None, ws_)
+        ops.sage_layer_bwd(graph, xs, a, None, None, ws_, ws_, None, torch.randn(n, 24, device=dev), has_bias=False)
+
+
 def test_masked_mse_matches_reference_fixture(ops):
     from helpers import load_golden
 
