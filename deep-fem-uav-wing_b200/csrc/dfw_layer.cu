@@ -112,3 +112,108 @@ extern "C" int dfw_sage_layer_bwd(const int32_t* rowptr_t, const int32_t* col_t,
                           nullptr, nullptr, nullptr, N, Hin, DFW_EP_TRANSPOSE_W | (res ? DFW_EP_RESIDUAL : 0), dtype, base + w.o_lin, w.lin_bytes,
                           stream);
 }
+
+// ---- one-call encoder / decoder MLP (dfw_mlp2_fwd / dfw_mlp2_bwd) ---------------------------------------
+//   mode DFW_MLP2_ENCODER (model.py:52-57):  hidden = relu(x W1^T + b1),           out = relu(hidden W2^T + b2)   [N, Hout]
+//   mode DFW_MLP2_DECODER (model.py:67-72):  hidden = dropout(relu(x W1^T + b1)),  out = hidden . w2 + b2         fp32 [N]
+//     (out_channels = 1: the 64 -> 1 projection is the row-dot epilogue of the first linear; w2 fp32 [Hmid], b2 fp32 [1])
+// Same launches as gnn/ops.py:LinearFn x 2 / DecoderTailFn, so the results are bit-identical to the model's path.
+namespace dfw {
+namespace {
+struct MlpWs {
+    size_t o_g2, o_gh, o_g1, o_epi, o_dw, o_lin, epi_bytes, dw_bytes, lin_bytes, total;
+};
+MlpWs carve_mlp_bwd(int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype, int mode, bool want_gx) {
+    const size_t e = dtype == DFW_F32 ? 4 : 2;
+    MlpWs w{};
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+    const bool enc = mode == DFW_MLP2_ENCODER;
+    w.o_g2 = take(enc ? (size_t)N * Hout * e : 0);   // dL/d(second pre-activation)
+    w.o_gh = take(enc ? (size_t)N * Hmid * e : 0);   // dL/d hidden
+    w.o_g1 = take((size_t)N * Hmid * e);             // dL/d(first pre-activation)
+    w.epi_bytes = std::max(dfw_epilogue_bwd_ws_bytes(N, Hmid), enc ? dfw_epilogue_bwd_ws_bytes(N, Hout) : (size_t)0);
+    w.o_epi = take(w.epi_bytes);
+    w.dw_bytes = std::max(dfw_linear_bwd_weight_ws_bytes(N, Hmid, K, 0), enc ? dfw_linear_bwd_weight_ws_bytes(N, Hout, Hmid, 0) : (size_t)0);
+    w.o_dw = take(w.dw_bytes);
+    w.lin_bytes = std::max(enc ? dfw_linear_ws_bytes(Hmid, Hout, 0, dtype) : (size_t)0, want_gx ? dfw_linear_ws_bytes(K, Hmid, 0, dtype) : (size_t)0);
+    w.o_lin = take(w.lin_bytes);
+    w.total = off + 256;
+    return w;
+}
+}  // namespace
+}  // namespace dfw
+
+extern "C" size_t dfw_mlp2_fwd_ws_bytes(int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype) {
+    if (N < 0 || K < 1 || Hmid < 1 || Hout < 1) return 0;
+    return std::max(dfw_linear_ws_bytes(Hmid, K, 0, dtype), dfw_linear_ws_bytes(Hout, Hmid, 0, dtype));
+}
+
+extern "C" int dfw_mlp2_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, float dropout_p, uint64_t seed,
+                            int flags, int mode, void* hidden, void* out, int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype,
+                            void* ws, size_t ws_bytes, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(mode == DFW_MLP2_ENCODER || mode == DFW_MLP2_DECODER, "dfw_mlp2_fwd: unknown mode %d", mode);
+    DFW_REQUIRE(x && w1 && w2 && out, "dfw_mlp2_fwd: null pointer");
+    const int seed_flag = flags & DFW_EP_SEED_IS_PTR;
+    if (mode == DFW_MLP2_ENCODER) {
+        DFW_REQUIRE(hidden, "dfw_mlp2_fwd: the encoder needs the hidden buffer");
+        int rc = dfw_linear_fwd(x, w1, K, nullptr, nullptr, 0, b1, nullptr, nullptr, 1e-5f, nullptr, 0.f, 0, hidden, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, N, Hmid, DFW_EP_RELU, dtype, ws, ws_bytes, stream);
+        if (rc) return rc;
+        return dfw_linear_fwd(hidden, w2, Hmid, nullptr, nullptr, 0, b2, nullptr, nullptr, 1e-5f, nullptr, 0.f, 0, out, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, N, Hout, DFW_EP_RELU, dtype, ws, ws_bytes, stream);
+    }
+    DFW_REQUIRE(Hout == 1, "dfw_mlp2_fwd: the decoder mode is the out_channels = 1 tail (Hout = %lld)", (long long)Hout);
+    const int f = DFW_EP_RELU | (dropout_p > 0.f ? (DFW_EP_DROPOUT | seed_flag) : 0);
+    // hidden may be NULL at inference (nothing to save): only the row dot leaves the kernel
+    return dfw_linear_fwd(x, w1, K, nullptr, nullptr, 0, b1, nullptr, nullptr, 1e-5f, nullptr, dropout_p, seed, hidden, nullptr, nullptr,
+                          reinterpret_cast<const float*>(w2), b2, reinterpret_cast<float*>(out), N, Hmid, f, dtype, ws, ws_bytes, stream);
+}
+
+extern "C" size_t dfw_mlp2_bwd_ws_bytes(int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype, int mode, int want_input_grad) {
+    if (N < 0 || K < 1 || Hmid < 1 || Hout < 1) return 0;
+    return dfw::carve_mlp_bwd(N, K, Hmid, Hout, dtype, mode, want_input_grad != 0).total;
+}
+
+extern "C" int dfw_mlp2_bwd(const void* x, const void* hidden, const void* out, const void* w1, const void* w2, const void* g_out,
+                            float dropout_p, uint64_t seed, int flags, int mode, void* g_x, float* dw1, float* db1, float* dw2, float* db2,
+                            int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype, void* ws, size_t ws_bytes, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(mode == DFW_MLP2_ENCODER || mode == DFW_MLP2_DECODER, "dfw_mlp2_bwd: unknown mode %d", mode);
+    DFW_REQUIRE(x && hidden && w1 && w2 && g_out && dw1 && dw2, "dfw_mlp2_bwd: null pointer");
+    const bool enc = mode == DFW_MLP2_ENCODER;
+    DFW_REQUIRE(!enc || out, "dfw_mlp2_bwd: the encoder needs its saved output (ReLU mask)");
+    DFW_REQUIRE(enc || Hout == 1, "dfw_mlp2_bwd: the decoder mode is the out_channels = 1 tail");
+    const MlpWs w = carve_mlp_bwd(N, K, Hmid, Hout, dtype, mode, g_x != nullptr);
+    DFW_REQUIRE(ws && ws_bytes >= w.total, "dfw_mlp2_bwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    char* base = base256(ws);
+    void* g1 = base + w.o_g1;
+    int rc;
+    if (enc) {
+        void* g2 = base + w.o_g2;
+        void* gh = base + w.o_gh;
+        // second linear: ReLU mask from the saved output, db2 = column sums, dW2 = g2^T hidden, g_hidden = g2 W2
+        rc = dfw_epilogue_bwd(g_out, nullptr, nullptr, nullptr, nullptr, out, nullptr, nullptr, 0.f, 0, g2, nullptr, nullptr, nullptr, nullptr, db2,
+                              N, Hout, DFW_EP_RELU, dtype, base + w.o_epi, w.epi_bytes, stream);
+        if (rc) return rc;
+        rc = dfw_linear_bwd_weight(g2, hidden, Hmid, nullptr, 0, dw2, nullptr, nullptr, N, Hout, dtype, 0, base + w.o_dw, w.dw_bytes, stream);
+        if (rc) return rc;
+        rc = dfw_linear_bwd_input(g2, w2, nullptr, nullptr, gh, N, Hout, Hmid, dtype, base + w.o_lin, dfw_linear_ws_bytes(Hmid, Hout, 0, dtype), stream);
+        if (rc) return rc;
+        // first linear
+        rc = dfw_epilogue_bwd(gh, nullptr, nullptr, nullptr, nullptr, hidden, nullptr, nullptr, 0.f, 0, g1, nullptr, nullptr, nullptr, nullptr, db1,
+                              N, Hmid, DFW_EP_RELU, dtype, base + w.o_epi, w.epi_bytes, stream);
+        if (rc) return rc;
+    } else {
+        // g_out is dL/d(row dot) fp32 [N]: ReLU / dropout backward of the hidden layer, d w2, d b2 and db1 in one pass
+        const int f = DFW_EP_RELU | (dropout_p > 0.f ? (DFW_EP_DROPOUT | (flags & DFW_EP_SEED_IS_PTR)) : 0);
+        rc = dfw_epilogue_bwd(nullptr, reinterpret_cast<const float*>(g_out), reinterpret_cast<const float*>(w2), nullptr, nullptr, hidden, nullptr,
+                              nullptr, dropout_p, seed, g1, nullptr, nullptr, dw2, db2, db1, N, Hmid, f, dtype, base + w.o_epi, w.epi_bytes, stream);
+        if (rc) return rc;
+    }
+    rc = dfw_linear_bwd_weight(g1, x, K, nullptr, 0, dw1, nullptr, nullptr, N, Hmid, dtype, 0, base + w.o_dw, w.dw_bytes, stream);
+    if (rc) return rc;
+    if (!g_x) return 0;
+    return dfw_linear_bwd_input(g1, w1, nullptr, nullptr, g_x, N, Hmid, K, dtype, base + w.o_lin, dfw_linear_ws_bytes(K, Hmid, 0, dtype), stream);
+}

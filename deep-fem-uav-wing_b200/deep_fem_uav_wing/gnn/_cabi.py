@@ -56,6 +56,13 @@ SIGNATURES = {
     "dfw_sage_layer_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "dfw_mlp2_fwd_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
+    "dfw_mlp2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_int, c_int, c_void_p, c_void_p,
+                             c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "dfw_mlp2_bwd_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int]),
+    "dfw_mlp2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int,
+                             c_void_p, c_size_t, c_void_p]),
     "dfw_masked_mse_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "dfw_masked_mse_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),

@@ -563,6 +563,62 @@ def sage_layer_bwd(graph: "CSRGraph", x, agg, pre, stats, w_l, w_r, ln, g_out, d
     return g_x, dw_l, db_l, dw_r, dgamma, dbeta
 
 
+MLP2_ENCODER, MLP2_DECODER = 0, 1
+
+
+def mlp2_fwd(x, w1, b1, w2, b2, mode, dropout_p=0.0, seed=0, save_hidden=True):
+    """One-call encoder / decoder MLP forward (``dfw_mlp2_fwd``).  Encoder: ``relu(relu(x W1^T + b1) W2^T + b2)``;
+    decoder (``out_channels = 1``): ``dropout(relu(x W1^T + b1)) . w2 + b2`` as fp32 ``[N]`` (``w2`` fp32 ``[Hmid]``, ``b2`` fp32 ``[1]``).
+    Returns ``(out, hidden)``."""
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    N, K = x.shape
+    Hmid = w1.shape[0]
+    dev, dt = x.device, x.dtype
+    seed_v, seed_flag = _seed_arg(seed)
+    if mode == MLP2_ENCODER:
+        Hout = w2.shape[0]
+        out = torch.empty(N, Hout, dtype=dt, device=dev)
+        save_hidden = True
+    else:
+        Hout = 1
+        out = torch.empty(N, dtype=torch.float32, device=dev)
+    hidden = torch.empty(N, Hmid, dtype=dt, device=dev) if save_hidden else None
+    ws_bytes = lib.dfw_mlp2_fwd_ws_bytes(N, K, Hmid, Hout, _dt(x))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dfw_mlp2_fwd(x.data_ptr(), w1.data_ptr(), _ptr(b1), w2.data_ptr(), _ptr(b2), float(dropout_p), seed_v, seed_flag, int(mode),
+                               _ptr(hidden), out.data_ptr(), N, K, Hmid, Hout, _dt(x), ws.data_ptr(), ws_bytes, _stream(x)))
+    LAUNCH_COUNTER["kernels"] += 2 if mode == MLP2_ENCODER else 1
+    return out, hidden
+
+
+def mlp2_bwd(x, hidden, out, w1, w2, g_out, mode, dropout_p=0.0, seed=0, want_input_grad=True, has_b1=True, has_b2=True):
+    """One-call encoder / decoder MLP backward (``dfw_mlp2_bwd``).  Returns ``(g_x, dw1, db1, dw2, db2)``."""
+    N, K = x.shape
+    Hmid = w1.shape[0]
+    dev = x.device
+    seed_v, seed_flag = _seed_arg(seed)
+    f32 = dict(dtype=torch.float32, device=dev)
+    g_out = g_out.contiguous()
+    if mode == MLP2_ENCODER:
+        Hout = w2.shape[0]
+        dw2, db2 = torch.empty(Hout, Hmid, **f32), (torch.empty(Hout, **f32) if has_b2 else None)
+    else:
+        Hout = 1
+        dw2, db2 = torch.empty(Hmid, **f32), (torch.empty(1, **f32) if has_b2 else None)
+    g_x = torch.empty(N, K, dtype=x.dtype, device=dev) if want_input_grad else None
+    dw1, db1 = torch.empty(Hmid, K, **f32), (torch.empty(Hmid, **f32) if has_b1 else None)
+    ws_bytes = lib.dfw_mlp2_bwd_ws_bytes(N, K, Hmid, Hout, _dt(x), int(mode), int(want_input_grad))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dfw_mlp2_bwd(x.data_ptr(), hidden.data_ptr(), _ptr(out), w1.data_ptr(), w2.data_ptr(), g_out.data_ptr(), float(dropout_p),
+                               seed_v, seed_flag, int(mode), _ptr(g_x), dw1.data_ptr(), _ptr(db1), dw2.data_ptr(), _ptr(db2),
+                               N, K, Hmid, Hout, _dt(x), ws.data_ptr(), ws_bytes, _stream(x)))
+    LAUNCH_COUNTER["kernels"] += 10 if mode == MLP2_ENCODER else 5
+    return g_x, dw1, db1, dw2, db2
+
+
 # ----------------------------------------------------------------------------------------------
 # autograd Functions
 # ----------------------------------------------------------------------------------------------

@@ -218,6 +218,29 @@ int dfw_sage_layer_bwd(const int32_t* rowptr_t, const int32_t* col_t, const floa
                        void* ws, size_t ws_bytes, dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * One-call encoder / decoder MLP - the launch sequences of (c), (d1)-(d3) behind one call each.
+ *   DFW_MLP2_ENCODER (model.py:52-57): hidden = relu(x W1^T + b1) [N,Hmid], out = relu(hidden W2^T + b2) [N,Hout];
+ *        w2 [Hout,Hmid] in the compute dtype, b2 fp32 [Hout].
+ *   DFW_MLP2_DECODER (model.py:67-72, out_channels = 1): hidden = dropout(relu(x W1^T + b1)) [N,Hmid] (nullable at
+ *        inference), out = hidden . w2 + b2 as fp32 [N]; w2 fp32 [Hmid], b2 fp32 [1] device pointer (nullable); Hout = 1.
+ *   bwd: g_out = dL/d out ([N,Hout] compute dtype / fp32 [N]); `out` = the encoder's saved output (ReLU mask; NULL for the
+ *        decoder); dw1 fp32 [Hmid,K], db1 fp32 [Hmid] (nullable), dw2 fp32 [Hout,Hmid] / [Hmid], db2 fp32 [Hout] / [1]
+ *        (nullable), g_x [N,K] (nullable).  flags: DFW_EP_SEED_IS_PTR or 0.
+ * ---------------------------------------------------------------------------------------- */
+enum { DFW_MLP2_ENCODER = 0, DFW_MLP2_DECODER = 1 };
+size_t dfw_mlp2_fwd_ws_bytes(int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype);
+int dfw_mlp2_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                 float dropout_p, uint64_t seed, int flags, int mode, void* hidden, void* out,
+                 int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype,
+                 void* ws, size_t ws_bytes, dfw_stream_t stream);
+size_t dfw_mlp2_bwd_ws_bytes(int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype, int mode, int want_input_grad);
+int dfw_mlp2_bwd(const void* x, const void* hidden, const void* out, const void* w1, const void* w2, const void* g_out,
+                 float dropout_p, uint64_t seed, int flags, int mode,
+                 void* g_x, float* dw1, float* db1, float* dw2, float* db2,
+                 int64_t N, int64_t K, int64_t Hmid, int64_t Hout, int dtype,
+                 void* ws, size_t ws_bytes, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Masked MSE (model.py:126-153) without boolean indexing / host sync.
  *   result fp32 [2]: [0] = loss (mean: sum/max(count,1); sum: sum), [1] = number of selected
  *   elements.  mask uint8 [N] (nullable = all rows).  pred/target fp32 or bf16 [N,C].

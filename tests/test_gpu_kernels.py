@@ -316,6 +316,51 @@ def test_one_call_sage_layer_equals_the_piecewise_path(ops, dtype, h, p):
         ops.sage_layer_bwd(graph, xs, a, None, None, ws_, ws_, None, torch.randn(n, 24, device=dev), has_bias=False)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_one_call_encoder_and_decoder_equal_the_piecewise_path(ops, dtype):
+    """``dfw_mlp2_fwd`` / ``dfw_mlp2_bwd`` vs the autograd Functions the model uses for its encoder
+    (two ``LinearFn``) and its decoder tail (``DecoderTailFn``): bit-identical outputs and gradients."""
+    torch.manual_seed(7)
+    n, dev = 3001, "cuda"
+
+    def leaf(*shape, scale=1.0):
+        return (torch.randn(*shape, device=dev) * scale).requires_grad_(True)
+
+    # encoder: Linear(10, 64) -> ReLU -> Linear(64, 128) -> ReLU (model.py:52-57)
+    x = torch.randn(n, 10, device=dev).to(dtype).requires_grad_(True)
+    w1, b1, w2, b2 = leaf(64, 10, scale=0.3), leaf(64), leaf(128, 64, scale=0.12), leaf(128)
+    g = torch.randn(n, 128, device=dev).to(dtype)
+    h1 = ops.LinearFn.apply(x, w1, b1, True, 0.0, 0)
+    h2 = ops.LinearFn.apply(h1, w2, b2, True, 0.0, 0)
+    h2.backward(g)
+    w1c, w2c = ops.cast(w1.detach(), dtype), ops.cast(w2.detach(), dtype)
+    out, hidden = ops.mlp2_fwd(x.detach(), w1c, b1.detach(), w2c, b2.detach(), ops.MLP2_ENCODER)
+    assert torch.equal(out, h2.detach()) and torch.equal(hidden, h1.detach())
+    g_x, dw1, db1, dw2, db2 = ops.mlp2_bwd(x.detach(), hidden, out, w1c, w2c, g, ops.MLP2_ENCODER)
+    assert torch.equal(g_x, x.grad) and torch.equal(dw1, w1.grad) and torch.equal(db1, b1.grad)
+    assert torch.equal(dw2, w2.grad) and torch.equal(db2, b2.grad)
+    g_x0, dw1b, _, _, _ = ops.mlp2_bwd(x.detach(), hidden, out, w1c, w2c, g, ops.MLP2_ENCODER, want_input_grad=False)
+    assert g_x0 is None and torch.equal(dw1b, dw1)  # the model's first layer: x needs no gradient
+
+    # decoder tail: Linear(128, 64) -> ReLU -> Dropout -> Linear(64, 1) (model.py:67-72)
+    h = torch.randn(n, 128, device=dev).to(dtype).requires_grad_(True)
+    w3, b3, w4, b4 = leaf(64, 128, scale=0.09), leaf(64), leaf(1, 64, scale=0.12), leaf(1)
+    p, seed = 0.1, 424242
+    y = ops.DecoderTailFn.apply(h, w3, b3, w4, b4, p, seed)
+    gy = torch.randn(n, 1, device=dev).to(dtype)
+    y.backward(gy)
+    w3c = ops.cast(w3.detach(), dtype)
+    w4f = w4.detach().float().reshape(-1).contiguous()
+    out, hidden = ops.mlp2_fwd(h.detach(), w3c, b3.detach(), w4f, b4.detach(), ops.MLP2_DECODER, dropout_p=p, seed=seed)
+    assert out.dtype == torch.float32 and out.shape == (n,)
+    assert torch.equal(out.unsqueeze(1) if dtype == torch.float32 else ops.cast(out.unsqueeze(1), dtype), y.detach())
+    g_h, dw3, db3, dw4, db4 = ops.mlp2_bwd(h.detach(), hidden, None, w3c, w4f, gy.reshape(-1).float(), ops.MLP2_DECODER, dropout_p=p, seed=seed)
+    assert torch.equal(g_h, h.grad) and torch.equal(dw3, w3.grad) and torch.equal(db3, b3.grad)
+    assert torch.equal(dw4.reshape(1, -1), w4.grad) and torch.equal(db4, b4.grad)
+    out_inf, hid_inf = ops.mlp2_fwd(h.detach(), w3c, b3.detach(), w4f, b4.detach(), ops.MLP2_DECODER, save_hidden=False)
+    assert hid_inf is None and out_inf.shape == (n,)  # inference: nothing saved, no dropout
+
+
 def test_masked_mse_matches_reference_fixture(ops):
     from helpers import load_golden
 
