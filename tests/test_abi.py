@@ -43,6 +43,24 @@ def test_size_queries_and_argument_errors_need_no_gpu():
                                        None, None, None, 4, 512, 0, 0, None, 0, None))
 
 
+def test_one_call_entry_points_validate_before_any_cuda_call():
+    from deep_fem_uav_wing.gnn import _cabi
+
+    lib = _cabi.lib
+    assert lib.dfw_sage_layer_fwd_ws_bytes(1000, 128, 128, 0) == lib.dfw_linear_ws_bytes(128, 128, 128, 0)
+    with_gx, without = lib.dfw_sage_layer_bwd_ws_bytes(1000, 128, 128, 0, 1), lib.dfw_sage_layer_bwd_ws_bytes(1000, 128, 128, 0, 0)
+    assert with_gx > without >= 1000 * 128 * 4  # g_y lives in the workspace, g_t only when an input gradient is wanted
+    assert lib.dfw_mlp2_bwd_ws_bytes(1000, 10, 64, 128, 0, 0, 1) > lib.dfw_mlp2_bwd_ws_bytes(1000, 128, 64, 1, 0, 1, 1) > 0
+    assert lib.dfw_sage_layer_fwd_ws_bytes(-1, 128, 128, 0) == 0 and lib.dfw_mlp2_fwd_ws_bytes(10, 0, 64, 1, 0) == 0
+    rc = lib.dfw_sage_layer_fwd(None, None, None, None, None, None, None, None, None, 1e-5, 0.0, 0, 0, None, None, None, None,
+                                10, 0, 128, 128, 0, None, 0, None)
+    assert rc != 0 and b"dfw_sage_layer_fwd" in lib.dfw_last_error()
+    rc = lib.dfw_mlp2_fwd(None, None, None, None, None, 0.0, 0, 0, 7, None, None, 10, 10, 64, 1, 0, None, 0, None)
+    assert rc != 0 and b"unknown mode" in lib.dfw_last_error()
+    rc = lib.dfw_csr_transpose(None, -1, 5, None, None, None, None, None, None, 0, None)
+    assert rc != 0 and b"negative" in lib.dfw_last_error()
+
+
 def test_product_path_refuses_cpu_tensors():
     import torch
 
