@@ -49,9 +49,22 @@ def peaks():
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
-def make_meshes(ids, kind="tri"):
-    from deep_fem_uav_wing.gnn import synth
+def _synth():
+    """gnn/synth.py imported BY FILE PATH: it is pure numpy, and importing it through the package would load libdfw_b200.so
+    into the CPU arm's process too."""
+    import importlib.util
 
+    mod = sys.modules.get("_dfw_synth")
+    if mod is None:
+        spec = importlib.util.spec_from_file_location("_dfw_synth", os.path.join(REPO, "deep-fem-uav-wing_b200", "deep_fem_uav_wing", "gnn", "synth.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_dfw_synth"] = mod
+        spec.loader.exec_module(mod)
+    return mod
+
+
+def make_meshes(ids, kind="tri"):
+    synth = _synth()
     gen = synth.surface_tri_wing if kind == "tri" else synth.tet_lattice_wing
     out = []
     for i in ids:
@@ -137,10 +150,11 @@ def timed_region(step_fn, steps, dist_on, device):
 # CPU arm (oracle port of the reference's PyG model)
 # --------------------------------------------------------------------------------------------
 def cpu_training_throughput(meshes, steps, warmup, threads=None):
+    """The reference's training step (train_gnn.py:50-60) on the host cores: oracle port of the PyG model, torch CPU fp32.
+    ``threads`` = None: every core of the box, set EXPLICITLY (torchrun exports OMP_NUM_THREADS=1)."""
     from oracle.sage_oracle import GraphSAGEModelRef, MaskedMSELossRef
 
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads if threads else (os.cpu_count() or 1))
     torch.manual_seed(42)
     model = GraphSAGEModelRef(10, HIDDEN, 1, LAYERS, DROPOUT).train()
     opt = torch.optim.AdamW(model.parameters(), lr=LR, weight_decay=WD)
@@ -182,19 +196,24 @@ def cpu_info():
     return {"os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads(), "cpu_model": model}
 
 
-def run_reference(args, rank, emit):
+def run_reference(args, rank, world, emit):
+    """Reference arm: the reference's own CPU implementation of the path (oracle port - PyG is not installable here) on ALL
+    host cores, on this arm's config/metric/unit.  A step = one 4 x 50k-node batch (the per-GPU batch of the config) through
+    fwd + bwd + AdamW: a bounded sample of the workload (~2 s per step on 16 cores).  --steps / --warmup are honoured; under
+    torchrun rank 0 alone runs (with every core: the thread count is set explicitly), the other ranks exit 0."""
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
-    meshes = make_meshes(range(BATCH * min(2, steps)), args.mesh)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    meshes = make_meshes(range(BATCH * min(4, steps)), args.mesh)
     value, ms = cpu_training_throughput(meshes, steps, warmup)
     info = cpu_info()
-    sample = f"{warmup} warm-up + {steps} timed fwd+bwd+AdamW steps of one 4x50k-node batch (cycling {len(meshes) // BATCH} batch(es)); oracle port of the PyG model, torch CPU fp32"
+    sample = (f"{warmup} warm-up + {steps} timed fwd+bwd+AdamW steps, each on one 4x50k-node batch (cycling {len(meshes) // BATCH} batch(es)); "
+              f"oracle port of the PyG model, torch CPU fp32, {info['torch_threads']} threads")
     line = {
         "impl": "reference", "metric": "train_meshes_per_sec", "value": value, "unit": "meshes/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": "meshes/s", "cores": info["torch_threads"], "kind": "port", "sample": sample, **info},
         "e2e": {"value": value, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -213,6 +232,226 @@ def workload_config(args, world):
 
 
 # --------------------------------------------------------------------------------------------
+# parity gates printed with the perf numbers - the oracle is used as the CHECKER only, next to the CPU baseline
+# --------------------------------------------------------------------------------------------
+def parity_gates(device):
+    """CSR bit-exact, forward max|d|/max|ref| and the worst per-parameter gradient rel-L2 of the product path against the
+    oracle on identical weights and one identical 20k-node mesh (config 1's size), dropout 0, H/L of the benchmarked model."""
+    from deep_fem_uav_wing.gnn import ops
+    from deep_fem_uav_wing.gnn.model import GraphSAGEModel, MaskedMSELoss
+    from oracle import csr_oracle_c
+    from oracle.sage_oracle import GraphSAGEModelRef, MaskedMSELossRef
+
+    mesh = _synth().surface_tri_wing(20000, seed=4242)
+    x, ei = torch.from_numpy(mesh["x"]), torch.from_numpy(mesh["edge_index"])
+    y, m = torch.from_numpy(mesh["y"]), torch.from_numpy(mesh["loss_mask"])
+    torch.manual_seed(42)
+    ref = GraphSAGEModelRef(10, HIDDEN, 1, LAYERS, dropout=0.0)
+    model = GraphSAGEModel(10, HIDDEN, 1, LAYERS, dropout=0.0)
+    model.load_state_dict(ref.state_dict(), strict=True)
+    model = model.to(device)
+    g = ops.get_graph(ei.to(device), x.shape[0], want_perm=True)
+    o = csr_oracle_c(mesh["edge_index"], x.shape[0])
+    csr_ok = bool(torch.equal(g.rowptr.cpu(), torch.from_numpy(o[0])) and torch.equal(g.col.cpu(), torch.from_numpy(o[1]))
+                  and torch.equal(g.perm.cpu(), torch.from_numpy(o[2])))
+    out_ref = ref(x, ei)
+    MaskedMSELossRef()(out_ref, y, m).backward()
+    out = model(x.to(device), ei.to(device))
+    MaskedMSELoss()(out, y.to(device), m.to(device)).backward()
+    fwd = ((out.detach().cpu() - out_ref.detach()).abs().max() / out_ref.detach().abs().max()).item()
+    ref64 = GraphSAGEModelRef(10, HIDDEN, 1, LAYERS, dropout=0.0).double()
+    ref64.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
+    MaskedMSELossRef()(ref64(x.double(), ei), y.double(), m).backward()
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300)).item()
+    worst32 = max(rel(p.grad.cpu(), pr.grad) for p, pr in zip(model.parameters(), ref.parameters()))
+    worst64 = max(rel(p.grad.cpu(), p64.grad) for p, p64 in zip(model.parameters(), ref64.parameters()))
+    oracle64 = max(rel(pr.grad, p64.grad) for pr, p64 in zip(ref.parameters(), ref64.parameters()))
+    ops.clear_graph_cache()
+    return {"csr_bit_exact": csr_ok, "fwd_rel_err": fwd, "grad_rel_l2_worst_vs_fp32_oracle": worst32,
+            "grad_rel_l2_worst_vs_fp64_oracle": worst64, "fp32_oracle_grad_rel_l2_vs_fp64": oracle64, "tolerance_fp32": 1e-5,
+            "mesh": "surface-tri 20k nodes, seed 4242", "hidden": HIDDEN, "layers": LAYERS,
+            "pass": bool(csr_ok and fwd < 1e-5 and worst64 < max(1e-5, 3 * oracle64))}
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE.json config 4: aggregation roofline on the 2M-node / 27M-edge tet lattice (N = 1 only)
+# --------------------------------------------------------------------------------------------
+CFG4_DIMS = (38, 114, 462)  # thickness x chord x span nodes: 2 001 384 nodes, 27.3 M directed edges
+
+
+def cfg4_lattice_device(dims, device, order="native", seed=42):
+    """The graph of ``synth.tet_lattice_wing(dims=...)`` (Kuhn 6-tet split of a hex lattice mapped into the wing: 14
+    neighbours per interior node; node id = (iz*ny + iy)*nx + ix) and its normalised positions, generated on the device
+    (27 M edges take ~20 s of numpy on the host).  ``order='random'``: nodes relabelled by a random permutation.
+    Same edge SET as the numpy generator (tests/test_bench_helpers.py)."""
+    nx, ny, nz = dims
+    n = nx * ny * nz
+    idx = torch.arange(n, device=device, dtype=torch.int64).view(nz, ny, nx)
+    parts = []
+    for dx, dy, dz in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 1, 1)):
+        a = idx[: nz - dz, : ny - dy, : nx - dx].reshape(-1)
+        b = idx[dz:, dy:, dx:].reshape(-1)
+        parts += [torch.stack([a, b]), torch.stack([b, a])]
+    ei = torch.cat(parts, dim=1)
+    g = torch.Generator(device=device).manual_seed(seed)
+    ei = ei[:, torch.randperm(ei.shape[1], device=device, generator=g)]  # edge order carries no information (dataset.py:39-63)
+    ix = (idx % nx).reshape(-1).double()
+    iy = ((idx // nx) % ny).reshape(-1).double()
+    iz = (idx // (nx * ny)).reshape(-1).double()
+    u, v, w = iy / max(ny - 1, 1), iz / max(nz - 1, 1), ix / max(nx - 1, 1) * 2.0 - 1.0
+    span, chord, sweep, tc = 1.5, 0.35, 15.0, 0.10
+    uc = u.clamp(0.0, 1.0)
+    naca = 5.0 * tc * (0.2969 * uc.sqrt() - 0.1260 * uc - 0.3516 * uc ** 2 + 0.2843 * uc ** 3 - 0.1015 * uc ** 4)
+    Y = v * span
+    pos = torch.stack([u * chord + Y * float(np.tan(np.deg2rad(sweep))), Y, w * naca * chord], dim=1).float()
+    lo, hi = pos.min(dim=0).values, pos.max(dim=0).values
+    rng_ = torch.where(hi - lo < 1e-8, torch.ones_like(lo), hi - lo)
+    pos_n = (pos - lo) / rng_  # dataset.py:130-136
+    if order == "random":
+        relabel = torch.randperm(n, device=device, generator=g)  # old id -> new id
+        inv = torch.empty_like(relabel)
+        inv[relabel] = torch.arange(n, device=device)
+        ei = relabel[ei]
+        pos_n = pos_n[inv]
+    elif order != "native":
+        raise ValueError(order)
+    return ei.contiguous(), pos_n.contiguous(), n
+
+
+def aggregation_cfg4(device, pk, iters=20):
+    """north_star's aggregation target (>= 60 % of HBM peak) is scored on config 4: one mean-aggregation launch over the
+    2M-node lattice, H = 256 bf16, native and random node order, L2 flushed between launches, CUDA events.
+    ``A_min = 2*N*H*b + 4*E + 4*(N+1)``."""
+    from deep_fem_uav_wing.gnn import ops
+
+    H = 256
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out = {"hidden": H, "dtype": "bf16", "lattice": list(CFG4_DIMS), "l2": "flushed between launches (256 MB write)", "iters": iters}
+    for order in ("native", "random"):
+        ei, pos_n, n = cfg4_lattice_device(CFG4_DIMS, device, order)
+        E = int(ei.shape[1])
+        x = torch.randn(n, H, device=device, generator=torch.Generator(device=device).manual_seed(1)).bfloat16()
+        amin = 2 * n * H * 2 + 4 * E + 4 * (n + 1)
+        ent = {"N": n, "E": E, "A_min_MB": round(amin / 1e6, 1), "A_gather_MB": round((E * H * 2 + n * H * 2 + 4 * E + 4 * (n + 1)) / 1e6, 1)}
+        for name, fn in ops.cfg4_aggregation_paths(ei, n, pos_n, x).items():
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize(device)
+                ts.append(a.elapsed_time(b) * 1e-3)
+            ts.sort()
+            med = ts[len(ts) // 2]
+            ent[name] = {"us": round(med * 1e6, 1), "p10_us": round(ts[len(ts) // 10] * 1e6, 1), "p90_us": round(ts[-1 - len(ts) // 10] * 1e6, 1),
+                         "achieved_GBps": round(amin / med / 1e9, 1), "frac": round(amin / med / 1e9 / pk["hbm_gbs"], 4)}
+        out[order] = ent
+        del ei, pos_n, x
+        ops.clear_graph_cache()
+        torch.cuda.empty_cache()
+    out["peak_GBps"] = pk["hbm_gbs"]
+    out["peak_source"] = pk["_source"]
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE.json config 5: design-screening batch inference, case list sharded over the ranks, no communication
+# --------------------------------------------------------------------------------------------
+def cfg5_block(device, rank, world, dist_on, n_cases=10000, nodes=20000, per_launch=16, distinct=48):
+    """Every rank takes ``case_ids[rank::world]`` (inference_gnn.py:380-398 loops the cases independently).  Per launch
+    ``per_launch`` packed cases (pos, normal, faces, globals - the content of the reference's three case files) go from
+    pinned host memory to the device, the graph is built there (``dfw_faces_to_csr`` + ``dfw_node_features``), one forward
+    (H = 128, L = 4, fp32) runs and the per-case mean prediction comes back to the host.  ``distinct`` different synthetic
+    cases per rank are cycled (generating 10k on the host would take minutes); everything else is per case."""
+    import torch.distributed as dist
+
+    from deep_fem_uav_wing.gnn import ops
+    from deep_fem_uav_wing.gnn.model import GraphSAGEModel
+
+    synth = _synth()
+    mine = len(range(rank, n_cases, world))
+    cases = []
+    for i in range(min(distinct, mine)):
+        m = synth.surface_tri_wing(nodes, seed=1000 + rank * distinct + i)
+        p = m["params"]
+        cases.append({"pos": torch.from_numpy(m["pos"]).pin_memory(), "normal": torch.from_numpy(m["normal"]).pin_memory(),
+                      "faces": torch.from_numpy(m["faces"].astype(np.int64)).pin_memory(), "n": m["num_nodes"],
+                      "gp": [p["span_m"], p["chord_m"], p["sweep_deg"], p["thickness_ratio"]]})
+    torch.manual_seed(42)
+    model = GraphSAGEModel(10, HIDDEN, 1, LAYERS).to(device).eval()
+    res_pin = torch.empty(per_launch, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=device)
+    h2d = 0
+
+    def stage(group):
+        nonlocal h2d
+        with torch.cuda.stream(copy_stream):
+            dev = []
+            for c in group:
+                dev.append((c["pos"].to(device, non_blocking=True), c["normal"].to(device, non_blocking=True),
+                            c["faces"].to(device, non_blocking=True), c["n"], c["gp"]))
+                h2d += c["pos"].numel() * 4 + c["normal"].numel() * 4 + c["faces"].numel() * 8
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dev, ev
+
+    def run(dev):
+        xs, fs, off, ptr = [], [], 0, [0]
+        for pos, nrm, faces, n, gp in dev:
+            x, _ = ops.node_features(pos, nrm, None, gp)  # per-mesh min-max normalisation (dataset.py:130-136)
+            xs.append(x)
+            fs.append(faces + off)
+            off += n
+            ptr.append(off)
+        # ONE graph build for the launch: the faces of the disjoint union (one 8-byte edge-count read per launch)
+        g, ei = ops.faces_to_graph(torch.cat(fs), off)
+        with torch.no_grad():
+            out = model(torch.cat(xs), ei)
+        if all(ptr[i + 1] - ptr[i] == ptr[1] for i in range(len(dev))):
+            means = out.view(len(dev), -1).mean(dim=1)
+        else:
+            means = torch.stack([out[ptr[i]:ptr[i + 1]].mean() for i in range(len(dev))])
+        res_pin[: len(dev)].copy_(means, non_blocking=True)
+        ops.clear_graph_cache()
+
+    n_launch = (mine + per_launch - 1) // per_launch
+    groups = [[cases[(l * per_launch + j) % len(cases)] for j in range(min(per_launch, mine - l * per_launch))] for l in range(n_launch)]
+    for l in range(2):  # warm-up
+        dev, ev = stage(groups[l % n_launch])
+        torch.cuda.current_stream(device).wait_event(ev)
+        run(dev)
+    torch.cuda.synchronize(device)
+    h2d = 0
+    k0 = ops.LAUNCH_COUNTER["kernels"]
+    if dist_on:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    nxt = stage(groups[0])
+    for l in range(n_launch):
+        dev, ev = nxt
+        if l + 1 < n_launch:
+            nxt = stage(groups[l + 1])  # H2D of the next launch overlaps this launch's graph build + forward
+        torch.cuda.current_stream(device).wait_event(ev)
+        run(dev)
+    b.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+    if dist_on:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"value": n_cases / (ms.item() * 1e-3), "unit": "meshes/s", "n_cases": n_cases, "cases_per_rank": mine, "nodes_per_case": nodes,
+            "nodes_per_sec": n_cases * nodes / (ms.item() * 1e-3), "ms_total": ms.item(), "cases_per_launch": per_launch, "hidden": HIDDEN,
+            "layers": LAYERS, "dtype": "f32", "h2d_bytes_per_case": h2d // max(mine, 1), "d2h_bytes_per_case": 4,
+            "gpu_launches": ops.LAUNCH_COUNTER["kernels"] - k0, "sharding": "case_ids[rank::world], no communication",
+            "path": "packed case (pos, normal, faces) in pinned host memory -> H2D -> dfw_node_features + dfw_faces_to_csr -> "
+                    "GraphSAGEModel forward -> per-case mean prediction D2H", "data": f"{len(cases)} distinct synthetic cases per rank, cycled"}
+
+
+# --------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -222,6 +461,7 @@ def main():
     ap.add_argument("--mesh", default="tri", choices=["tri", "tet"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the tet-batch, config-4 aggregation and config-5 blocks")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs (both arms)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -239,7 +479,7 @@ def main():
         os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     if args.impl == "reference":
-        run_reference(args, rank, emit)
+        run_reference(args, rank, world, emit)
         return
 
     import torch.distributed as dist
@@ -258,6 +498,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus or not dist_on, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    # ---- parity gates, printed with the perf numbers (rank 0; the oracle is the checker) ----------
+    gates = parity_gates(device) if (rank == 0 and not args.no_cpu_baseline) else None
 
     # ---- data: this rank's shard of the 200 meshes (mesh id = rank + k*world) -----------------
     steps, warmup = args.steps, args.warmup
@@ -355,17 +598,22 @@ def main():
     # DRAM traffic per launch of the same kernel on the same shapes, from the committed `ncu --set full` captures
     # (tools/ncu_capture_all.sh -> tools/ncu_summary.py --json); null when no capture of that kernel is on file
     traffic, traffic_src = None, None
-    tpath = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")
-    cap = {"aggregate": "r01b_agg_cfg2", "aggregate_bwd": "r01b_aggs_cfg2", "linear_fwd": "r01b_lin_fwd_fp32",
-           "linear_bwd_input": "r01b_lin_fwd_fp32", "linear_bwd_weight": "r01b_dw_fp32", "epilogue_bwd": "r01b_epi_bwd_fp32"}
-    if os.path.exists(tpath):
+    # (an EARLIER capture on another box: `_capture` in that file names the commit and date it was taken at; the DRAM bytes
+    # of a kernel depend on its shapes and tiling, not on the box, so they stay valid until the kernel's tiling changes)
+    tpath = next((q for q in (os.path.join(REPO, "profiles", f) for f in ("r02_ncu_traffic.json", "r01_ncu_traffic.json")) if os.path.exists(q)), None)
+    cap = {"aggregate": "agg_cfg2", "aggregate_bwd": "aggs_cfg2", "linear_fwd": "lin_fwd_fp32",
+           "linear_bwd_input": "lin_fwd_fp32", "linear_bwd_weight": "dw_fp32", "epilogue_bwd": "epi_bwd_fp32"}
+    if tpath is not None:
         tj = json.load(open(tpath))
+        find = lambda key: next((v for k, v in tj.items() if isinstance(v, dict) and k.endswith(key)), None) if key else None
         for name, ent in kernels.items():
-            c = tj.get(cap.get(name, ""))
+            c = find(cap.get(name))
             if c:
                 ent["ncu_dram_bytes_per_launch"] = c["dram_bytes"]
-        if cap.get(dom) in tj:
-            traffic, traffic_src = tj[cap[dom]]["dram_bytes"], f"profiles/r01_ncu_traffic.json:{cap[dom]}"
+        c = find(cap.get(dom))
+        if c:
+            traffic = c["dram_bytes"]
+            traffic_src = {"file": os.path.relpath(tpath, REPO), "entry": cap[dom], "capture": tj.get("_capture", "round 1 (r01b captures, commit 5c226f5 era)")}
     roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": d["hbm_frac"], "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": summ[dom]["bytes"] / summ[dom]["calls"], "peak_source": pk["_source"],
@@ -426,13 +674,43 @@ def main():
                        "incl. on-device CSR build -> MaskedMSELoss -> backward -> AdamW (one CUDA graph per batch shape, gradient all-reduce captured with it) -> loss copied to pinned host memory and read "
                        "(every step, one step behind the launch front)"}
 
+    # ---- the other graph family of config 2 (BASELINE.md scores both): tet-lattice batch, degree ~14 ----------------------
+    tet = None
+    if args.mesh == "tri" and not args.no_extras:
+        tdatas = [to_data(m) for m in make_meshes([5000 + rank * 2 * BATCH + i for i in range(2 * BATCH)], "tet")]
+        tres = [Batch.from_data_list(tdatas[i * BATCH:(i + 1) * BATCH]).to(device) for i in range(2)]
+        for b in tres:
+            ops.get_graph(b.edge_index, b.x.shape[0]).transpose()
+        for i in range(3):
+            train_step(tres[i % 2])
+        tsteps = min(steps, 20)
+        if not args.no_graph:
+            treplays = [rstep.capture_resident(b.x, b.edge_index, b.y, b.loss_mask)[0] for b in tres]
+            for r_ in treplays:
+                r_()
+            ms_tet = timed_region(lambda i: treplays[i % 2](), tsteps, dist_on, device)
+        else:
+            ms_tet = timed_region(lambda i: train_step(tres[i % 2]), tsteps, dist_on, device)
+        tet = {"value": BATCH * tsteps * world / (ms_tet * 1e-3), "unit": "meshes/s", "ms_per_step": ms_tet / tsteps, "steps": tsteps,
+               "nodes_per_batch": int(tres[0].x.shape[0]), "edges_per_batch": int(tres[0].edge_index.shape[1]),
+               "what": "same training step, device-resident, on 4 x 50k-node TET-lattice meshes (degree ~14), 2 batches cycled"}
+
+    # ---- config 5 (every N) and config 4's aggregation roofline (N = 1) --------------------------------------------------
+    cfg5 = agg4 = None
+    if not args.no_extras:
+        cfg5 = cfg5_block(device, rank, world, dist_on)
+        if world == 1:
+            agg4 = aggregation_cfg4(device, pk)
+
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms = cpu_training_throughput(meshes[:BATCH], steps=2, warmup=1)
+        v, ms = cpu_training_throughput(meshes[:2 * BATCH], steps=8, warmup=2)
         info = cpu_info()
+        v1, ms1 = cpu_training_throughput(meshes[:BATCH], steps=1, warmup=0, threads=1)
         cpu = {"value": v, "unit": "meshes/s", "cores": info["torch_threads"], "kind": "port", "ms_per_step": ms,
-               "sample": "1 warm-up + 2 timed fwd+bwd+AdamW steps on the first 4x50k-node batch of this workload (oracle port of the PyG model, torch CPU fp32)",
+               "sample": "2 warm-up + 8 timed fwd+bwd+AdamW steps over the first two 4x50k-node batches of this workload (oracle port of the PyG model, torch CPU fp32, all host threads)",
+               "one_thread": {"value": v1, "unit": "meshes/s", "ms_per_step": ms1, "sample": "1 timed step, torch.set_num_threads(1)"},
                **info}
 
     if rank == 0:
@@ -443,8 +721,8 @@ def main():
             "nodes_per_sec": value * NODES, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "infer": infer,
             "aggregation": {"kernel": "dfw_sage_aggregate (forward mean, this workload)", "achieved_GBps": kernels.get("aggregate", {}).get("achieved_GBps"),
-                            "hbm_frac": kernels.get("aggregate", {}).get("hbm_frac"),
-                            "config4": "2M nodes / 27M edges / H=256 bf16: profiles/r01_cfg4_2M_bf16.jsonl (tools/bench_configs.py cfg4)"},
+                            "hbm_frac": kernels.get("aggregate", {}).get("hbm_frac")},
+            "aggregation_cfg4": agg4, "cfg5": cfg5, "tet_batch": tet, "parity": gates,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         }
         emit(line)

@@ -210,6 +210,9 @@ def graph_dict_to_data(g: dict) -> Data:
     )
 
 
+PROCESSED_FORMAT = "dfw_b200/records/v1"  # tag of the processed cache files written by WingStressDataset.process
+
+
 class WingStressDataset:
     """In-memory dataset of wing graphs (``dataset.py:168-328``), PyG-free.
 
@@ -227,8 +230,25 @@ class WingStressDataset:
         split_idx = {"train": 0, "val": 1, "test": 2}[split]
         if not all(Path(p).exists() for p in self.processed_paths):
             self.process()
-        records = torch.load(self.processed_paths[split_idx], weights_only=False)
+        records = self._load_records(self.processed_paths[split_idx])
+        if records is None:  # not written by this package (or an older layout): rebuild our own cache files
+            self.process()
+            records = self._load_records(self.processed_paths[split_idx])
+            if records is None:
+                raise RuntimeError(f"{self.processed_paths[split_idx]} is not a {PROCESSED_FORMAT} file even after re-processing")
         self._data = [Data(**r) for r in records]
+
+    @staticmethod
+    def _load_records(path):
+        """Records of one of OUR processed files, or None when the payload is something else (e.g. PyG's collated
+        ``(data, slices)`` tuple, which the reference writes to ``train_s{seed}.pt`` in the same directory)."""
+        try:
+            payload = torch.load(path, weights_only=False)
+        except Exception:
+            return None
+        if isinstance(payload, dict) and payload.get("format") == PROCESSED_FORMAT and isinstance(payload.get("records"), list):
+            return payload["records"]
+        return None
 
     @property
     def raw_dir(self) -> str:
@@ -244,7 +264,10 @@ class WingStressDataset:
 
     @property
     def processed_file_names(self) -> list[str]:
-        return [f"train_s{self.seed}.pt", f"val_s{self.seed}.pt", f"test_s{self.seed}.pt"]
+        # NOT the reference's ``train_s{seed}.pt`` (dataset.py:219-224): those hold PyG's collated ``(data, slices)`` pair and
+        # need torch_geometric to unpickle; ours hold a tagged list of tensor dicts.  Both can live in the same
+        # ``data/processed/gnn`` directory without breaking each other.
+        return [f"train_s{self.seed}_dfw.pt", f"val_s{self.seed}_dfw.pt", f"test_s{self.seed}_dfw.pt"]
 
     @property
     def processed_paths(self) -> list[str]:
@@ -302,7 +325,7 @@ class WingStressDataset:
 
         Path(self.processed_dir).mkdir(parents=True, exist_ok=True)
         for part, path in zip(parts, self.processed_paths):
-            torch.save([data_list[i].to_dict() for i in part], path)
+            torch.save({"format": PROCESSED_FORMAT, "records": [data_list[i].to_dict() for i in part]}, path)
 
         split_info = {
             "seed": self.seed, "split_ratio": self.split_ratio, "n_total": len(data_list),

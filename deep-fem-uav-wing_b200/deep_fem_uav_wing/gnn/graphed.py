@@ -30,7 +30,8 @@ class GraphedTrainStep:
         self.kernels_per_replay = 0
         dev = next(model.parameters()).device
         if model.device_seeds is None:
-            g = torch.Generator().manual_seed(torch.initial_seed())
+            rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+            g = torch.Generator().manual_seed((torch.initial_seed() + 0x9E3779B9 * rank) & 0x7FFFFFFFFFFFFFFF)  # per-rank masks
             model.device_seeds = torch.randint(0, 2**62, (model.num_layers + 1,), generator=g, dtype=torch.int64).to(dev)
         self._pool = None
 

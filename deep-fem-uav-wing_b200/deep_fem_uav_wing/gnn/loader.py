@@ -201,19 +201,21 @@ class DataLoader:
     # stream, plus an in-place offset add for edge_index.  No host-side concatenation (a 28 MB memcpy per
     # step on one core was slower than the whole GPU step).  One batch of prefetch: the copy of batch i+1
     # overlaps the compute of batch i; the consumer only waits on the copy's event.
-    def pin_dataset(self) -> None:
-        """Page-lock every (host) graph of the dataset once so that all later H2D copies are asynchronous.
-        Done eagerly at the first iteration: pinning is slow (milliseconds per mesh) and must not land in a step."""
+    def pin_dataset(self, indices=None) -> None:
+        """Page-lock the (host) graphs this loader will draw - ``indices`` (default: this rank's shard of the current
+        epoch, ``_indices()``), never the whole dataset: under torchrun every rank would otherwise pin all N cases although
+        it consumes N / world of them.  Done eagerly at the first iteration of an epoch: pinning is slow (milliseconds per
+        mesh) and must not land in a step; graphs pinned in earlier epochs stay pinned."""
         if self._pinned is None:
             self._pinned = {}
-        for i in range(len(self.dataset)):
+        for i in (self._indices() if indices is None else indices):
             if i not in self._pinned:
                 d = self._select(self.dataset[i])
                 self._pinned[i] = d if (getattr(d, "x", None) is not None and d.x.is_pinned()) else d.pin_memory()
 
     def _pinned_item(self, i):
         if self._pinned is None or i not in self._pinned:
-            self.pin_dataset()
+            self.pin_dataset([i])
         return self._pinned[i]
 
     def _device_collate(self, items, dev):

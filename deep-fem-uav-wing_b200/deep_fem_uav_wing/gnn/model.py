@@ -29,8 +29,12 @@ HAS_TORCH_GEOMETRIC = False  # not needed; kept because callers of the reference
 
 
 def _next_seed() -> int:
-    # CPU generator: follows torch.manual_seed (train_gnn.py:128) without touching the device
-    return int(torch.randint(0, 2**62, (1,)).item())
+    # CPU generator: follows torch.manual_seed (train_gnn.py:128) without touching the device.  Under torchrun every rank
+    # seeds that generator identically, so the rank is mixed in: ranks must not all drop the same units of their meshes.
+    seed = int(torch.randint(0, 2**62, (1,)).item())
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        seed ^= (torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
+    return seed
 
 
 class SAGEConv(nn.Module):
@@ -104,6 +108,8 @@ class GraphSAGEModel(nn.Module):
         """fp32 (default) or bf16 activations; parameters stay fp32 master copies."""
         if dtype not in (torch.float32, torch.bfloat16):
             raise TypeError("compute dtype must be torch.float32 or torch.bfloat16")
+        if dtype == torch.bfloat16 and self.hidden_channels % 8 != 0:  # 16-byte rows for the 128-bit gathers
+            raise ValueError(f"dfw_b200: bf16 activations need hidden_channels % 8 == 0 (got {self.hidden_channels})")
         self.compute_dtype = dtype
         return self
 

@@ -261,7 +261,7 @@ def node_features(pos: torch.Tensor, normal: torch.Tensor, stress: torch.Tensor 
 
 
 _CSR_CACHE: "OrderedDict[tuple, CSRGraph]" = OrderedDict()
-_CSR_CACHE_SIZE = 64
+_CSR_CACHE_SIZE = 16  # loaders create a new edge_index tensor per step: a long LRU only pins dead batches' CSRs in HBM
 
 
 def _cache_key(edge_index: torch.Tensor, num_nodes: int):
@@ -331,6 +331,14 @@ def aggregate_scaled(rowptr, col, src_scale, x, label="aggregate_bwd"):
                                             N, E, H, _dt(x), _stream(x)))
     LAUNCH_COUNTER["kernels"] += 1
     return out
+
+
+def cfg4_aggregation_paths(edge_index, num_nodes, pos, x):
+    """The aggregation paths bench.py times on BASELINE.json config 4: name -> zero-argument callable running ONE mean
+    aggregation of ``x`` over the graph (one-time graph preparation happens here, outside the callables)."""
+    g = get_graph(edge_index, num_nodes)
+    paths = {"gather": lambda: aggregate(g.rowptr, g.col, g.inv_deg, x)}
+    return paths
 
 
 def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=False, residual=None, dropout_p=0.0, seed=0,
@@ -674,7 +682,9 @@ class SageConvFn(torch.autograd.Function):
         wl, wr = _w(w_l, dt), _w(w_r, dt)
         bl = _f32(b_l.detach()) if b_l is not None else None
         agg = aggregate(graph.rowptr, graph.col, graph.inv_deg, x)
-        needs_grad = any(ctx.needs_input_grad[:6])
+        # needs_input_grad reflects requires_grad even under torch.no_grad(): without the grad-mode test eval / predict()
+        # would still write the pre-LayerNorm tensor and the statistics of every layer
+        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[:6])
         if fused_tail:
             ln = (_f32(gamma.detach()), _f32(beta.detach()))
             out, pre, stats, _ = linear_fwd(agg, wl, x, wr, bias=bl, ln=ln, eps=eps, relu=True, residual=x,
@@ -733,7 +743,7 @@ class LinearFn(torch.autograd.Function):
         wc = _w(w, dt)
         out, _, _, _ = linear_fwd(x, wc, bias=_f32(b.detach()) if b is not None else None, relu=relu, dropout_p=dropout_p,
                                   seed=seed)
-        if any(ctx.needs_input_grad[:3]):
+        if torch.is_grad_enabled() and any(ctx.needs_input_grad[:3]):
             ctx.relu, ctx.dropout_p, ctx.seed, ctx.has_bias = relu, dropout_p, seed, b is not None
             ctx.save_for_backward(x, wc, out if relu else None)
         return out
@@ -772,7 +782,7 @@ class DecoderTailFn(torch.autograd.Function):
         dt = h.dtype
         w3c = _w(w3, dt)
         w4f = _f32(w4.detach()).reshape(-1)
-        needs_grad = any(ctx.needs_input_grad[:5])
+        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[:5])
         b4f = _f32(b4.detach()).reshape(-1) if b4 is not None else None
         hid, _, _, rd = linear_fwd(h, w3c, bias=_f32(b3.detach()) if b3 is not None else None, relu=True, dropout_p=dropout_p,
                                    seed=seed, rowdot=(w4f, b4f), want_out=needs_grad)

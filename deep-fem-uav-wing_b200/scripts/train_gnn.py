@@ -130,9 +130,12 @@ def main():
         dist.barrier()
     train_ds, val_ds, test_ds = (WingStressDataset(root, split=s, seed=args.seed) for s in ("train", "val", "test"))
     log(f"[Train] Train: {len(train_ds)}, Val: {len(val_ds)}, Test: {len(test_ds)}")
-    train_loader = DataLoader(train_ds, batch_size=args.batch_size, shuffle=True, device=device, rank=rank, world_size=world, seed=args.seed)
-    val_loader = DataLoader(val_ds, batch_size=args.batch_size, shuffle=False, device=device)
-    test_loader = DataLoader(test_ds, batch_size=args.batch_size, shuffle=False, device=device)
+    # only the fields the step reads cross PCIe (pos, disp, stress_vm_raw, global_params* stay on the host)
+    keys = ("x", "edge_index", "y", "loss_mask")
+    train_loader = DataLoader(train_ds, batch_size=args.batch_size, shuffle=True, device=device, rank=rank, world_size=world, seed=args.seed,
+                              keys=keys)
+    val_loader = DataLoader(val_ds, batch_size=args.batch_size, shuffle=False, device=device, keys=keys)
+    test_loader = DataLoader(test_ds, batch_size=args.batch_size, shuffle=False, device=device, keys=keys)
 
     model = GraphSAGEModel(10, args.hidden_channels, 1, args.num_layers, args.dropout).to(device)
     if args.dtype == "bf16":

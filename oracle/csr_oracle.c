@@ -52,9 +52,12 @@ int oracle_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src
     return 0;
 }
 
-/* out[i,:] = scale_i * sum_{k in row i} x[col[k],:]   (scale_i = inv_deg[i] or 1) ; fp32 */
+/* out[i,:] = scale_i * sum_{k in row i} x[col[k],:]   (scale_i = inv_deg[i] or 1) ; fp32
+ * Rows are independent, so the row loop may run on several host threads (OpenMP): every row is still summed
+ * sequentially in CSR order by one thread, i.e. the result does not depend on the thread count. */
 void oracle_csr_aggregate_f32(const int32_t* rowptr, const int32_t* col, const float* inv_deg,
                               const float* x, float* out, int64_t N, int64_t H) {
+#pragma omp parallel for schedule(static, 1024)
     for (int64_t i = 0; i < N; ++i) {
         float* o = out + i * H;
         for (int64_t h = 0; h < H; ++h) o[h] = 0.0f;

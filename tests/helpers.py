@@ -42,3 +42,17 @@ def canon_edges(ei):
     ei = np.asarray(ei)
     order = np.lexsort((ei[0], ei[1]))
     return ei[:, order]
+
+
+def record(name, **vals):
+    """Append the ACHIEVED numbers of a parity gate to ``gpurun_out/r02_parity_gates.jsonl`` (copied to ``profiles/`` after a
+    GPU run) so that the margin of every tolerance is visible, not only pass/fail."""
+    import json
+
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "r02_parity_gates.jsonl"), "a") as f:
+            f.write(json.dumps({"gate": name, **{k: (float(v) if isinstance(v, (int, float, np.floating)) else v) for k, v in vals.items()}}) + "\n")
+    except OSError:
+        pass

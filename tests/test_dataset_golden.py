@@ -94,6 +94,27 @@ def test_dataset_and_loader_roundtrip():
         assert b.ptr.tolist() == [0, d0.num_nodes, d0.num_nodes + d1.num_nodes]
 
 
+def test_processed_cache_coexists_with_reference_format_files():
+    """The reference writes PyG's collated ``(data, slices)`` tuple to ``data/processed/gnn/{split}_s{seed}.pt``
+    (dataset.py:219-224); ours are separate, tagged files, and a foreign payload under OUR name is rebuilt, not crashed on."""
+    from deep_fem_uav_wing.gnn.dataset import PROCESSED_FORMAT
+
+    with tempfile.TemporaryDirectory() as td:
+        for s in range(4):
+            synth.write_case_files(synth.surface_tri_wing(120 + 8 * s, seed=s), Path(td))
+        proc = Path(td) / "data" / "processed" / "gnn"
+        proc.mkdir(parents=True)
+        for sp in ("train", "val", "test"):  # what a project root already processed by the reference holds
+            torch.save(({"x": torch.zeros(3, 10)}, {"x": torch.tensor([0, 3])}), proc / f"{sp}_s42.pt")
+        ds = WingStressDataset(td, split="train", seed=42)
+        assert len(ds) == 2
+        assert isinstance(torch.load(proc / "train_s42.pt", weights_only=False), tuple)  # the reference's file is untouched
+        ours = torch.load(proc / "train_s42_dfw.pt", weights_only=False)
+        assert ours["format"] == PROCESSED_FORMAT and len(ours["records"]) == 2
+        torch.save(({"x": torch.zeros(3, 10)}, {}), proc / "train_s42_dfw.pt")  # a foreign payload under our name
+        assert len(WingStressDataset(td, split="train", seed=42)) == 2
+
+
 def test_loader_sharding_is_a_partition():
     data = [Data(x=torch.zeros(3, 10), edge_index=torch.zeros(2, 0, dtype=torch.long), tag=i) for i in range(10)]
     seen = []
