@@ -53,21 +53,50 @@ int oracle_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by_src
 }
 
 /* out[i,:] = scale_i * sum_{k in row i} x[col[k],:]   (scale_i = inv_deg[i] or 1) ; fp32
- * Rows are independent, so the row loop may run on several host threads (OpenMP): every row is still summed
- * sequentially in CSR order by one thread, i.e. the result does not depend on the thread count. */
-void oracle_csr_aggregate_f32(const int32_t* rowptr, const int32_t* col, const float* inv_deg,
-                              const float* x, float* out, int64_t N, int64_t H) {
-#pragma omp parallel for schedule(static, 1024)
-    for (int64_t i = 0; i < N; ++i) {
-        float* o = out + i * H;
+ * Rows are independent, so contiguous row ranges run on several host threads (pthreads; no OpenMP runtime in the
+ * image): every row is still summed sequentially in CSR order by one thread, so the result does not depend on the
+ * thread count. */
+#include <pthread.h>
+#include <unistd.h>
+
+typedef struct {
+    const int32_t* rowptr; const int32_t* col; const float* inv_deg; const float* x; float* out;
+    int64_t r0, r1, H;
+} agg_job;
+
+static void* agg_rows(void* arg) {
+    const agg_job* j = (const agg_job*)arg;
+    const int64_t H = j->H;
+    for (int64_t i = j->r0; i < j->r1; ++i) {
+        float* o = j->out + i * H;
         for (int64_t h = 0; h < H; ++h) o[h] = 0.0f;
-        for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
-            const float* r = x + (int64_t)col[k] * H;
+        for (int32_t k = j->rowptr[i]; k < j->rowptr[i + 1]; ++k) {
+            const float* r = j->x + (int64_t)j->col[k] * H;
             for (int64_t h = 0; h < H; ++h) o[h] += r[h];
         }
-        if (inv_deg) {
-            float s = inv_deg[i];
+        if (j->inv_deg) {
+            float s = j->inv_deg[i];
             for (int64_t h = 0; h < H; ++h) o[h] *= s;
         }
     }
+    return 0;
+}
+
+void oracle_csr_aggregate_f32(const int32_t* rowptr, const int32_t* col, const float* inv_deg,
+                              const float* x, float* out, int64_t N, int64_t H) {
+    long nproc = sysconf(_SC_NPROCESSORS_ONLN);
+    int T = (int)(nproc < 1 ? 1 : (nproc > 32 ? 32 : nproc));
+    if (N * H < (1 << 22)) T = 1;
+    agg_job jobs[32];
+    pthread_t th[32];
+    const int64_t per = (N + T - 1) / T;
+    for (int t = 0; t < T; ++t) {
+        agg_job j = {rowptr, col, inv_deg, x, out, t * per < N ? t * per : N, (t + 1) * per < N ? (t + 1) * per : N, H};
+        jobs[t] = j;
+    }
+    for (int t = 1; t < T; ++t)
+        if (pthread_create(&th[t], 0, agg_rows, &jobs[t]) != 0) { agg_rows(&jobs[t]); th[t] = 0; jobs[t].r0 = jobs[t].r1; }
+    agg_rows(&jobs[0]);
+    for (int t = 1; t < T; ++t)
+        if (jobs[t].r0 != jobs[t].r1 || th[t]) pthread_join(th[t], 0);
 }
