@@ -670,7 +670,33 @@ def _side_stream(device) -> torch.cuda.Stream:
 
 
 
-class SageConvFn(torch.autograd.Function):
+import threading
+
+_TLS = threading.local()
+
+
+class _Fn(torch.autograd.Function):
+    """autograd.Function whose ``forward`` can ask whether the CALLER had grad mode on.  ``ctx.needs_input_grad`` reflects
+    ``requires_grad`` of the inputs even under ``torch.no_grad()``, and inside ``forward`` grad mode is always off, so
+    without this eval / ``predict()`` would still write the tensors only a backward needs (pre-LayerNorm values,
+    statistics, the decoder's hidden layer) - extra HBM passes on the inference path."""
+
+    @classmethod
+    def apply(cls, *args):
+        prev = getattr(_TLS, "grad", None)
+        _TLS.grad = torch.is_grad_enabled()
+        try:
+            return super().apply(*args)
+        finally:
+            _TLS.grad = prev
+
+
+def _caller_grad_enabled() -> bool:
+    g = getattr(_TLS, "grad", None)
+    return True if g is None else bool(g)
+
+
+class SageConvFn(_Fn):
     """SAGEConv forward/backward (mean aggregation + lin_l + lin_r), optionally with the
     model's LayerNorm -> ReLU -> dropout -> residual tail fused in (``model.py:90-95``)."""
 
@@ -684,7 +710,7 @@ class SageConvFn(torch.autograd.Function):
         agg = aggregate(graph.rowptr, graph.col, graph.inv_deg, x)
         # needs_input_grad reflects requires_grad even under torch.no_grad(): without the grad-mode test eval / predict()
         # would still write the pre-LayerNorm tensor and the statistics of every layer
-        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[:6])
+        needs_grad = _caller_grad_enabled() and any(ctx.needs_input_grad[:6])
         if fused_tail:
             ln = (_f32(gamma.detach()), _f32(beta.detach()))
             out, pre, stats, _ = linear_fwd(agg, wl, x, wr, bias=bl, ln=ln, eps=eps, relu=True, residual=x,
@@ -732,7 +758,7 @@ class SageConvFn(torch.autograd.Function):
         return g_x, dwl, dbl, dwr, dgamma, dbeta, None, None, None, None, None
 
 
-class LinearFn(torch.autograd.Function):
+class LinearFn(_Fn):
     """``relu?(x W^T + b)`` (+ dropout): encoder / decoder linears (``model.py:52-57,67-72``)."""
 
     @staticmethod
@@ -743,7 +769,7 @@ class LinearFn(torch.autograd.Function):
         wc = _w(w, dt)
         out, _, _, _ = linear_fwd(x, wc, bias=_f32(b.detach()) if b is not None else None, relu=relu, dropout_p=dropout_p,
                                   seed=seed)
-        if torch.is_grad_enabled() and any(ctx.needs_input_grad[:3]):
+        if _caller_grad_enabled() and any(ctx.needs_input_grad[:3]):
             ctx.relu, ctx.dropout_p, ctx.seed, ctx.has_bias = relu, dropout_p, seed, b is not None
             ctx.save_for_backward(x, wc, out if relu else None)
         return out
@@ -771,7 +797,7 @@ class LinearFn(torch.autograd.Function):
         return g_x, dw, db, None, None, None
 
 
-class DecoderTailFn(torch.autograd.Function):
+class DecoderTailFn(_Fn):
     """``Linear(H,64) -> ReLU -> Dropout -> Linear(64,1)`` in one kernel (``model.py:67-72``):
     the 64 -> 1 projection is a row dot product in the epilogue of the first linear."""
 
@@ -782,7 +808,7 @@ class DecoderTailFn(torch.autograd.Function):
         dt = h.dtype
         w3c = _w(w3, dt)
         w4f = _f32(w4.detach()).reshape(-1)
-        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[:5])
+        needs_grad = _caller_grad_enabled() and any(ctx.needs_input_grad[:5])
         b4f = _f32(b4.detach()).reshape(-1) if b4 is not None else None
         hid, _, _, rd = linear_fwd(h, w3c, bias=_f32(b3.detach()) if b3 is not None else None, relu=True, dropout_p=dropout_p,
                                    seed=seed, rowdot=(w4f, b4f), want_out=needs_grad)
