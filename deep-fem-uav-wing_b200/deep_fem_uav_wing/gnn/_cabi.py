@@ -34,6 +34,12 @@ SIGNATURES = {
                                    c_int, c_void_p]),
     "dfw_sage_aggregate_scaled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
                                           c_void_p]),
+    "dfw_agg_plan_sizes": (c_int, [c_int64, c_int64, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
+    "dfw_agg_plan_max_block_edges": (c_int, []),
+    "dfw_agg_plan_build": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
+    "dfw_sage_aggregate_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                      c_void_p]),
     "dfw_linear_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                c_float, c_void_p, c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),

@@ -78,17 +78,22 @@ class GraphedTrainStep:
         cached for ``edge_index`` stays outside the graph.  Returns ``(replay, loss)``: ``replay()`` runs one training
         step on this batch, ``loss`` is the static tensor it fills.  Used for pre-staged data sets (the whole
         data set fits in HBM) where a step should cost one launch and no copies."""
+        # the CSR (and its transpose) is built - or fetched from the cache - BEFORE the capture and handed to the model as an
+        # object: the CUDA graph holds raw pointers into it, so it must stay alive with the replay closure whatever the
+        # LRU cache of ops.get_graph evicts later
+        csr = ops.get_graph(edge_index, int(x.shape[0]))
+        csr.transpose()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         if self.ddp is None:
             self.optimizer.zero_grad(set_to_none=True)
         k0 = ops.LAUNCH_COUNTER["kernels"]
         with torch.cuda.graph(g, pool=self._pool, capture_error_mode="thread_local"):
-            sloss = self._step(x, edge_index, y, mask)
+            sloss = self._step(x, csr, y, mask)
         kernels = ops.LAUNCH_COUNTER["kernels"] - k0
         if self._pool is None:
             self._pool = g.pool()
-        keep = (x, edge_index, y, mask)  # the graph holds raw pointers to them
+        keep = (x, edge_index, y, mask, csr)  # the graph holds raw pointers to them
 
         def replay(_g=g, _keep=keep, _k=kernels):
             _g.replay()

@@ -120,7 +120,6 @@ class GraphSAGEModel(nn.Module):
         graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, x.shape[0])
         cd = self.compute_dtype
         out_dtype = x.dtype
-        h = ops.cast_ad(x, cd)
         p = float(self.dropout) if self.training else 0.0
         if p > 0.0 and self.device_seeds is not None:  # seeds live on the device (see gnn/graphed.py)
             layer_seed = [self.device_seeds[i:i + 1] for i in range(self.num_layers)]
@@ -131,7 +130,12 @@ class GraphSAGEModel(nn.Module):
             dec_seed = seed + 0x7F4A7C15
 
         enc0, enc2 = self.encoder[0], self.encoder[2]
+        # The first linear reads the 10 raw features in THEIR dtype: normalised positions rounded to bf16 (8 bits) move a
+        # trained model's output by percents where the stress field is steep (wing tip), while the layer is 10-wide and
+        # costs nothing in fp32; its 64-wide output is what enters the compute dtype.
+        h = x if (x.dtype == torch.float32 and cd == torch.bfloat16) else ops.cast_ad(x, cd)
         h = ops.LinearFn.apply(h, enc0.weight, enc0.bias, True, 0.0, 0)
+        h = ops.cast_ad(h, cd)
         h = ops.LinearFn.apply(h, enc2.weight, enc2.bias, True, 0.0, 0)
 
         for i, (conv, norm) in enumerate(zip(self.convs, self.norms)):

@@ -333,11 +333,75 @@ def aggregate_scaled(rowptr, col, src_scale, x, label="aggregate_bwd"):
     return out
 
 
+@dataclass
+class AggPlan:
+    """Block plan of a CSR for ``dfw_sage_aggregate_tc`` (per 128-row block: distinct source rows + a 16-bit slot per edge)."""
+
+    num_nodes: int
+    blk_meta: torch.Tensor
+    plan_src: torch.Tensor
+    plan_rec: torch.Tensor
+    plan_slot: torch.Tensor
+    status: torch.Tensor          # uint64-as-int64 [2] on the device: [0] max edges of a block, [1] total staged rows
+    usable: bool | None = None    # resolved by ``check()`` (one 16-byte D2H read)
+    staged_rows_per_row: float | None = None
+
+    def check(self) -> bool:
+        if self.usable is None:
+            st = self.status.cpu().tolist()
+            self.usable = int(st[0]) <= int(lib.dfw_agg_plan_max_block_edges())
+            self.staged_rows_per_row = float(st[1]) / max(self.num_nodes, 1)
+        return self.usable
+
+
+def build_agg_plan(rowptr: torch.Tensor, col: torch.Tensor, num_nodes: int) -> AggPlan:
+    """``dfw_agg_plan_build``: one-time preparation of a graph for the tensor-core aggregation (3 launches, no host sync)."""
+    import ctypes
+
+    N, E, dev = int(num_nodes), int(col.shape[0]), rowptr.device
+    nb, sc, tc_ = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    check(lib.dfw_agg_plan_sizes(N, E, ctypes.byref(nb), ctypes.byref(sc), ctypes.byref(tc_)))
+    nb, sc, tc_ = nb.value, sc.value, tc_.value
+    blk_meta = torch.empty(max(4 * nb, 4), dtype=torch.int32, device=dev)
+    plan_src = torch.empty(sc, dtype=torch.int32, device=dev)
+    plan_rec = torch.empty(max(136 * nb, 8), dtype=torch.int16, device=dev)
+    plan_slot = torch.empty(tc_, dtype=torch.int16, device=dev)
+    status = torch.zeros(2, dtype=torch.int64, device=dev)
+    ws = torch.empty(max(8 * nb, 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev), _prof("agg_plan_build", 8 * E + 4 * (N + 1)):
+        check(lib.dfw_agg_plan_build(rowptr.data_ptr(), _ptr(col), N, E, blk_meta.data_ptr(), plan_src.data_ptr(), plan_rec.data_ptr(),
+                                     plan_slot.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(rowptr)))
+    LAUNCH_COUNTER["kernels"] += 3
+    return AggPlan(N, blk_meta, plan_src, plan_rec, plan_slot, status)
+
+
+def aggregate_tc(plan: AggPlan, row_scale, x, num_edges: int = 0):
+    """``dfw_sage_aggregate_tc``: mean (``row_scale = inv_deg``) or sum (None) of neighbour rows, bf16, H in {64, 128, 256}."""
+    _require_cuda(x, "x")
+    if x.dtype != torch.bfloat16:
+        raise TypeError(f"aggregate_tc takes bfloat16 rows, got {x.dtype}")
+    x = x.contiguous()
+    N, H = x.shape
+    if N != plan.num_nodes:
+        raise ValueError(f"plan was built for {plan.num_nodes} rows, x has {N}")
+    out = torch.empty_like(x)
+    amin = 2 * N * H * 2 + 4 * num_edges + 4 * (N + 1)
+    with torch.cuda.device(x.device), _prof("aggregate_tc", amin):
+        check(lib.dfw_sage_aggregate_tc(plan.blk_meta.data_ptr(), plan.plan_src.data_ptr(), plan.plan_rec.data_ptr(), plan.plan_slot.data_ptr(),
+                                        _ptr(row_scale), x.data_ptr(), out.data_ptr(), N, H, DFW_BF16, _stream(x)))
+    LAUNCH_COUNTER["kernels"] += 1
+    return out
+
+
 def cfg4_aggregation_paths(edge_index, num_nodes, pos, x):
     """The aggregation paths bench.py times on BASELINE.json config 4: name -> zero-argument callable running ONE mean
     aggregation of ``x`` over the graph (one-time graph preparation happens here, outside the callables)."""
     g = get_graph(edge_index, num_nodes)
     paths = {"gather": lambda: aggregate(g.rowptr, g.col, g.inv_deg, x)}
+    if x.dtype == torch.bfloat16 and x.shape[1] in (64, 128, 256):
+        plan = build_agg_plan(g.rowptr, g.col, num_nodes)
+        if plan.check():
+            paths["tensor_core_blocks"] = lambda: aggregate_tc(plan, g.inv_deg, x, g.num_edges)
     return paths
 
 

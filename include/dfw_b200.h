@@ -121,6 +121,30 @@ int dfw_sage_aggregate_scaled(const int32_t* rowptr, const int32_t* col, const f
                               int64_t N, int64_t E, int64_t H, int dtype, dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (b') the same mean / sum aggregation for bf16 rows on the tensor cores (block-sparse product; refined meshes, BASELINE.json
+ *     config 4).  Replaces the same PyG expression as dfw_sage_aggregate (index_select + scatter_add_ + divide behind
+ *     SAGEConv(aggr='mean'), call site model.py:90).  Rows are cut into blocks of 128 consecutive rows; a one-time PLAN of the
+ *     CSR lists per block its distinct source rows and a 16-bit slot per edge; per block  OUT[128,H] = ADJ[128,S] . X[S,H]
+ *     runs as tcgen05.mma with fp32 accumulation (ADJ = edge multiplicities: exact products), row_scale in the epilogue.
+ *     Result = the CSR-order fp32 sum up to the association order of the fp32 additions (<= 1 bf16 ulp after rounding).
+ *
+ *     dfw_agg_plan_sizes: array lengths for a graph of N rows / E edges: blk_meta int32 [4*nblocks], plan_src int32 [src_cap],
+ *       plan_rec uint16 [136*nblocks], plan_slot uint16 [slot_cap]; ws of dfw_agg_plan_build: 8 bytes per block.
+ *     dfw_agg_plan_build: status uint64 [2] (device): [0] = largest number of edges in a block - the plan is USABLE only if
+ *       it is <= dfw_agg_plan_max_block_edges(); [1] = total number of staged rows (sum of S over the blocks: the locality
+ *       measure, staged rows per output row = [1] / N).  No host synchronisation.
+ *     dfw_sage_aggregate_tc: x, out bf16 [N,H], H in {64,128,256}; row_scale fp32 [N] (inv_deg: mean) or NULL (sum).
+ * ---------------------------------------------------------------------------------------- */
+int dfw_agg_plan_sizes(int64_t N, int64_t E, int64_t* nblocks, int64_t* src_cap, int64_t* slot_cap);
+int dfw_agg_plan_max_block_edges(void);
+int dfw_agg_plan_build(const int32_t* rowptr, const int32_t* col, int64_t N, int64_t E,
+                       int32_t* blk_meta, int32_t* plan_src, uint16_t* plan_rec, uint16_t* plan_slot,
+                       uint64_t* status, void* ws, size_t ws_bytes, dfw_stream_t stream);
+int dfw_sage_aggregate_tc(const int32_t* blk_meta, const int32_t* plan_src, const uint16_t* plan_rec, const uint16_t* plan_slot,
+                          const float* row_scale, const void* x, void* out,
+                          int64_t N, int64_t H, int dtype, dfw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * (c) fused node-wise linear:
  *        y   = a1 . w1^T (+ a2 . w2^T) (+ bias)                       [N,Hout]
  *        out = (residual +) dropout(relu(layernorm(y)))               per `flags`
