@@ -1,0 +1,115 @@
+"""Tensor-core block-sparse aggregation (GPU, through the C ABI): the device-built block plan against the numpy design oracle
+(``oracle/blocked_agg_oracle.py``) bit for bit, and ``dfw_sage_aggregate_tc`` against the plain-C CSR aggregation
+(``oracle/csr_oracle.c``) - mean and sum, H in {64, 128, 256}, ragged last blocks, isolated rows, duplicate edges, long rows,
+random graphs with poor locality (many chunks per block)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import TOL_BF16, record, rel_max
+from oracle import csr_aggregate_c, csr_oracle_c
+from oracle.blocked_agg_oracle import build_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from deep_fem_uav_wing.gnn import ops as _ops
+
+    return _ops
+
+
+def _graphs():
+    from deep_fem_uav_wing.gnn import synth
+
+    rng = np.random.default_rng(0)
+    out = {}
+    out["tet_5k"] = (synth.tet_lattice_wing(5000, seed=1)["edge_index"], None)
+    m = synth.surface_tri_wing(3000, seed=2)
+    out["tri_3k"] = (m["edge_index"], m["num_nodes"])
+    n = 1000
+    ei = rng.integers(0, n, size=(2, 9000)).astype(np.int64)  # random: duplicates, self loops, ~14 chunks per block
+    ei[1, :300] = 5  # one long row
+    ei = ei[:, ei[1] != 77]  # one isolated row
+    out["random_1k"] = (ei, n)
+    out["single_row"] = (np.array([[0, 0, 0], [0, 0, 0]], dtype=np.int64), 1)
+    out["no_edges"] = (np.zeros((2, 0), dtype=np.int64), 300)
+    out["ragged_129"] = (rng.integers(0, 129, size=(2, 700)).astype(np.int64), 129)
+    return out
+
+
+@pytest.mark.parametrize("name", ["tet_5k", "tri_3k", "random_1k", "single_row", "no_edges", "ragged_129"])
+def test_block_plan_matches_design_oracle(ops, name):
+    ei, n = _graphs()[name]
+    n = int(ei.max()) + 1 if n is None else n
+    rowptr, col, _, _ = csr_oracle_c(ei, n)
+    plan = ops.build_agg_plan(torch.from_numpy(rowptr).cuda(), torch.from_numpy(col).cuda(), n)
+    assert plan.check()
+    blk_ptr, blk_src, slot = build_blocks(rowptr, col, 128)
+    meta = plan.blk_meta.cpu().numpy().reshape(-1, 4)
+    src = plan.plan_src.cpu().numpy()
+    rec = plan.plan_rec.cpu().numpy().view(np.uint16).reshape(-1, 136)
+    slots = plan.plan_slot.cpu().numpy().view(np.uint16)
+    nb = (n + 127) // 128
+    assert meta.shape[0] >= nb
+    total = 0
+    for b in range(nb):
+        s_off, S, t_off, ne = (int(v) for v in meta[b])
+        r0, r1 = 128 * b, min(128 * b + 128, n)
+        e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+        assert ne == e1 - e0 and S == blk_ptr[b + 1] - blk_ptr[b] and s_off % 64 == 0 and t_off % 8 == 0
+        assert np.array_equal(src[s_off:s_off + S], blk_src[blk_ptr[b]:blk_ptr[b + 1]])  # ascending distinct sources
+        pad = (max(S, 1) + 63) // 64 * 64
+        assert np.all(src[s_off + S:s_off + pad] == (src[s_off + S - 1] if S else 0))
+        assert np.array_equal(slots[t_off:t_off + ne], slot[e0:e1])
+        want_off = np.minimum(rowptr[r0:r0 + 129] if r0 + 129 <= n + 1 else np.concatenate([rowptr[r0:n + 1], np.full(r0 + 129 - n - 1, e1)]), e1) - e0
+        assert np.array_equal(rec[b, :129], want_off.astype(np.uint16)) and rec[b, 129] == S
+        total += S
+    assert abs(plan.staged_rows_per_row * n - total) < 0.5
+
+
+@pytest.mark.parametrize("h", [64, 128, 256])
+@pytest.mark.parametrize("name", ["tet_5k", "tri_3k", "random_1k", "single_row", "no_edges", "ragged_129"])
+def test_aggregate_tc_matches_c_oracle(ops, name, h):
+    ei, n = _graphs()[name]
+    n = int(ei.max()) + 1 if n is None else n
+    rng = np.random.default_rng(h)
+    x = torch.from_numpy(rng.standard_normal((n, h)).astype(np.float32)).bfloat16()
+    rowptr, col, _, inv = csr_oracle_c(ei, n)
+    g = ops.get_graph(torch.from_numpy(ei).cuda(), n)
+    plan = ops.build_agg_plan(g.rowptr, g.col, n)
+    assert plan.check()
+    for scale, inv_np in ((g.inv_deg, inv), (None, None)):  # mean, then plain sum
+        ref = torch.from_numpy(csr_aggregate_c(rowptr, col, inv_np, x.float().numpy()))
+        got = ops.aggregate_tc(plan, scale, x.cuda(), g.num_edges)
+        assert got.dtype == torch.bfloat16 and got.shape == (n, h)
+        gf = got.float().cpu()
+        assert torch.isfinite(gf).all()
+        err = rel_max(gf, ref) if ref.abs().max() > 0 else float(gf.abs().max())
+        mism = int((got.cpu() != ref.bfloat16()).sum())
+        record("aggregate_tc_vs_c_oracle", graph=name, H=h, mean=scale is not None, rel_max=err, bf16_mismatches=mism, elements=n * h)
+        assert err < TOL_BF16
+        # association order of fp32 additions only: at most one bf16 ulp of the result's magnitude
+        assert (gf - ref).abs().max().item() <= 2.0 ** -7 * max(ref.abs().max().item(), 1e-30)
+        assert torch.equal(got, ops.aggregate_tc(plan, scale, x.cuda(), g.num_edges))  # deterministic
+        same = ops.aggregate(g.rowptr, g.col, scale, x.cuda())
+        assert rel_max(gf, same.float().cpu()) < 2.0 ** -7 if ref.abs().max() > 0 else True
+
+
+def test_aggregate_tc_rejects_what_it_cannot_take(ops):
+    from deep_fem_uav_wing.gnn import _cabi
+
+    ei = np.array([[0, 1], [1, 0]], dtype=np.int64)
+    g = ops.get_graph(torch.from_numpy(ei).cuda(), 2)
+    plan = ops.build_agg_plan(g.rowptr, g.col, 2)
+    with pytest.raises(TypeError):
+        ops.aggregate_tc(plan, None, torch.zeros(2, 64, device="cuda"))
+    with pytest.raises(_cabi.DfwError, match="64, 128 or 256"):
+        ops.aggregate_tc(plan, None, torch.zeros(2, 96, device="cuda", dtype=torch.bfloat16))
+    # a block with more edges than the plan holds is reported, not mis-computed
+    n = 200
+    hub = np.stack([np.arange(5000) % n, np.zeros(5000, dtype=np.int64)]).astype(np.int64)
+    gh = ops.get_graph(torch.from_numpy(hub).cuda(), n)
+    ph = ops.build_agg_plan(gh.rowptr, gh.col, n)
+    assert not ph.check()
