@@ -333,7 +333,7 @@ def aggregation_cfg4(device, pk, iters=20):
         x = torch.randn(n, H, device=device, generator=torch.Generator(device=device).manual_seed(1)).bfloat16()
         amin = 2 * n * H * 2 + 4 * E + 4 * (n + 1)
         ent = {"N": n, "E": E, "A_min_MB": round(amin / 1e6, 1), "A_gather_MB": round((E * H * 2 + n * H * 2 + 4 * E + 4 * (n + 1)) / 1e6, 1)}
-        for name, fn in ops.cfg4_aggregation_paths(ei, n, pos_n, x).items():
+        for name, (fn, info) in ops.cfg4_aggregation_paths(ei, n, pos_n, x).items():
             for _ in range(3):
                 fn()
             ts = []
@@ -348,7 +348,9 @@ def aggregation_cfg4(device, pk, iters=20):
             ts.sort()
             med = ts[len(ts) // 2]
             ent[name] = {"us": round(med * 1e6, 1), "p10_us": round(ts[len(ts) // 10] * 1e6, 1), "p90_us": round(ts[-1 - len(ts) // 10] * 1e6, 1),
-                         "achieved_GBps": round(amin / med / 1e9, 1), "frac": round(amin / med / 1e9 / pk["hbm_gbs"], 4)}
+                         "achieved_GBps": round(amin / med / 1e9, 1), "frac": round(amin / med / 1e9 / pk["hbm_gbs"], 4), **info}
+        best = min((k for k in ent if isinstance(ent[k], dict)), key=lambda k: ent[k]["us"])
+        ent["best"] = {"path": best, "us": ent[best]["us"], "frac": ent[best]["frac"]}
         out[order] = ent
         del ei, pos_n, x
         ops.clear_graph_cache()

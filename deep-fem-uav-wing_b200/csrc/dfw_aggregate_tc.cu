@@ -46,11 +46,13 @@ using namespace tc;
 constexpr int kBlockRows = 128;
 constexpr int kChunk = 64;        // staged source rows (K) per pipeline stage
 constexpr int kRecU16 = 136;      // uint16 per block record: row offsets [0..128], S at [129]; 272 B
-constexpr int kPlanCap = 4096;    // edges per block the plan (and the kernel's slot buffer) can hold
+constexpr int kPlanCap = 3072;    // edges per block the plan (and the kernel's slot buffer) can hold: mean degree <= 24
+constexpr int kSortCap = 4096;    // power of two >= kPlanCap (bitonic sort in the plan build)
 constexpr int kIdxRing = 8;
 constexpr int kThreads = 640;
 constexpr int kProducerWarps = 8;
 constexpr int kMaxStages = 4;
+constexpr int kStagingBoxes = 1;  // shared memory goes to the pipeline (bytes in flight bound this kernel), not to the epilogue
 
 struct Params {
     const int4* blk_meta;      // [nblocks] {src_off, S, slot_off, ne}
@@ -73,8 +75,8 @@ __host__ __device__ inline Layout carve(int H, int stages) {
     L.b_bytes = (uint32_t)kChunk * (uint32_t)H * 2u;  // H/64 boxes of [64 rows x 128 B]
     L.a_bytes = kBlockRows * 128u;                    // [128 rows x 64 k] bf16
     L.stage = L.b_bytes + L.a_bytes;
-    L.staging = L.stage * (uint32_t)stages;           // 2 boxes [128 rows x 128 B] for the TMA stores
-    L.blkbuf = L.staging + 2u * kBlockRows * 128u;
+    L.staging = L.stage * (uint32_t)stages;           // kStagingBoxes boxes [128 rows x 128 B] for the TMA stores
+    L.blkbuf = L.staging + (uint32_t)kStagingBoxes * kBlockRows * 128u;
     L.blkbuf_bytes = 288u + kPlanCap * 2u;            // record (272 B, padded) + slots
     L.idx = L.blkbuf + 2u * L.blkbuf_bytes;
     L.flags = L.idx + kIdxRing * kChunk * 4u;
@@ -235,10 +237,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
             tmem_ld32_issue(t_row, ra);
             for (int cb = 0; cb < H / 64; ++cb) {
                 tmem_ld32_issue(t_row + cb * 64 + 32, rb);
-                // the store that used this staging box two boxes ago must have finished reading it
-                if (et == 0) tma_store_wait_read<1>();
+                // the store that last used this staging box must have finished reading it
+                if (et == 0) tma_store_wait_read<kStagingBoxes - 1>();
                 epi_bar();
-                uint8_t* box = stg + (size_t)(n_store & 1) * (kBlockRows * 128);
+                uint8_t* box = stg + (size_t)(n_store % kStagingBoxes) * (kBlockRows * 128);
                 tmem_ld_wait(ra);
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
 __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int4* __restrict__ meta,
                                                      int32_t* __restrict__ plan_src, uint16_t* __restrict__ plan_rec, uint16_t* __restrict__ plan_slot,
                                                      unsigned long long* __restrict__ status /*[0] max edges of a block, [1] sum of S*/) {
-    __shared__ unsigned long long key[kPlanCap];
+    __shared__ unsigned long long key[kSortCap];
     __shared__ int wsum[8];
     __shared__ int s_total;
     const int b = blockIdx.x;

@@ -90,6 +90,7 @@ class GraphSAGEModel(nn.Module):
         self.num_layers = num_layers
         self.dropout = dropout
         self.compute_dtype = torch.float32
+        self.node_reorder = "auto"  # 'auto' | 'always' | 'never': k-d relabelling of large meshes for bf16 inference (ops.get_inference_graph)
         self.device_seeds = None  # int64 CUDA tensor [num_layers + 1]: dropout seeds read by the kernels (CUDA-graph mode)
 
         self.encoder = nn.Sequential(
@@ -117,9 +118,24 @@ class GraphSAGEModel(nn.Module):
         """``x [N, in_channels]``, ``edge_index [2, E]`` int64 -> ``[N, out_channels]``.
         ``batch`` is accepted and ignored, as in the reference (``model.py:74``)."""
         ops._require_cuda(x, "x")
-        graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, x.shape[0])
         cd = self.compute_dtype
         out_dtype = x.dtype
+        restore = None
+        n_nodes = int(x.shape[0])
+        if (cd == torch.bfloat16 and not torch.is_grad_enabled() and isinstance(edge_index, torch.Tensor)
+                and self.hidden_channels in ops.TC_AGG_WIDTHS and n_nodes >= ops.TC_AGG_MIN_NODES
+                and not torch.cuda.is_current_stream_capturing()):
+            # large static mesh, bf16 inference (BASELINE.json config 4): block plan for the tensor-core aggregation and,
+            # where the given numbering has poor locality, a one-time k-d relabelling of the nodes - applied here to the
+            # 10-wide input and undone on the 1-wide output, so no [N, H] tensor is ever permuted
+            pos = x[:, :3] if (self.node_reorder != "never" and self.in_channels >= 3) else None
+            ig = ops.get_inference_graph(edge_index, n_nodes, pos=pos, reorder=self.node_reorder)
+            graph = ig.graph
+            if ig.order is not None:
+                x = x.index_select(0, ig.order)
+                restore = ig.new_id
+        else:
+            graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, n_nodes)
         p = float(self.dropout) if self.training else 0.0
         if p > 0.0 and self.device_seeds is not None:  # seeds live on the device (see gnn/graphed.py)
             layer_seed = [self.device_seeds[i:i + 1] for i in range(self.num_layers)]
@@ -148,7 +164,8 @@ class GraphSAGEModel(nn.Module):
         else:
             hid = ops.LinearFn.apply(h, dec0.weight, dec0.bias, True, p, dec_seed)
             out = ops.LinearFn.apply(hid, dec3.weight, dec3.bias, False, 0.0, 0)
-        return ops.cast_ad(out, out_dtype)
+        out = ops.cast_ad(out, out_dtype)
+        return out if restore is None else out.index_select(0, restore)
 
     def predict(self, data):
         """Convenience method for inference (``model.py:101-112``)."""

@@ -125,6 +125,7 @@ class CSRGraph:
     _pending: list = field(default_factory=list)
     skipped_faces: torch.Tensor | None = None
     status_t: torch.Tensor | None = None  # int32 [3] of dfw_csr_transpose ([2] = 1: the graph was not symmetric)
+    plan: "AggPlan | None" = None         # block plan for dfw_sage_aggregate_tc (large-mesh bf16 inference)
 
     def transpose(self):
         if self.rowptr_t is None:
@@ -393,15 +394,151 @@ def aggregate_tc(plan: AggPlan, row_scale, x, num_edges: int = 0):
     return out
 
 
-def cfg4_aggregation_paths(edge_index, num_nodes, pos, x):
-    """The aggregation paths bench.py times on BASELINE.json config 4: name -> zero-argument callable running ONE mean
-    aggregation of ``x`` over the graph (one-time graph preparation happens here, outside the callables)."""
+def locality_order(pos: torch.Tensor, edge_index: torch.Tensor, leaf: int = 128, max_sample_edges: int = 1 << 22) -> torch.Tensor:
+    """Node relabelling that makes blocks of ``leaf`` consecutive rows spatially compact: ``new_id[old_id]`` (int64, on the
+    device of ``pos``).  One-time graph preparation for the blocked aggregation (``dfw_sage_aggregate_tc`` stages the union
+    of a block's neighbours: 4.2 rows per output row on the config-4 lattice in its native numbering, 2.75 in this order,
+    13.7 in a random numbering).
+
+    k-d ordering by recursive MEDIAN bisection: every segment of the current order longer than ``leaf`` is sorted along the
+    axis of its largest extent - measured in hops, i.e. coordinates divided by the mean coordinate difference along the mesh
+    edges, so element anisotropy (thin wing sections) does not bias the choice - and cut at the multiple of ``leaf`` nearest
+    its middle.  Splitting by RANK adapts to the node density (a Morton code of quantised coordinates does not: where the
+    thickness tapers to zero whole columns fall into one cell).  log2(N / leaf) rounds of two stable sorts, all on the
+    device; the coordinates are the model's own input features ``x[:, :3]`` (normalised positions, reference
+    ``dataset.py:130-145``), so the permutation is applied to the 10-wide input and undone on the 1-wide output."""
+    n = int(pos.shape[0])
+    dev = pos.device
+    if n <= leaf:
+        return torch.arange(n, device=dev)
+    p = pos[:, :3].to(torch.float32)
+    E = int(edge_index.shape[1])
+    if E > 0:
+        stride = max(1, E // max_sample_edges)
+        es = edge_index[:, ::stride]
+        hop = (p[es[0]] - p[es[1]]).abs().mean(dim=0)
+        hop = torch.where(hop > 0, hop, torch.ones_like(hop))
+        p = p / hop
+    order = torch.arange(n, device=dev)
+    bounds = torch.tensor([0, n], device=dev, dtype=torch.int64)
+    while True:
+        seg_len = bounds[1:] - bounds[:-1]
+        big = seg_len > leaf
+        if not bool(big.any()):
+            break
+        nseg = int(seg_len.numel())
+        seg = torch.repeat_interleave(torch.arange(nseg, device=dev), seg_len, output_size=n)
+        cur = p[order]
+        idx3 = seg[:, None].expand(-1, 3)
+        mn = torch.full((nseg, 3), float("inf"), device=dev).scatter_reduce_(0, idx3, cur, "amin")
+        mx = torch.full((nseg, 3), float("-inf"), device=dev).scatter_reduce_(0, idx3, cur, "amax")
+        ax = torch.argmax(mx - mn, dim=1)
+        coord = cur.gather(1, ax[seg][:, None]).squeeze(1)
+        i1 = torch.argsort(coord, stable=True)
+        i2 = torch.argsort(seg[i1], stable=True)
+        order = order[i1[i2]]
+        a, b = bounds[:-1][big], bounds[1:][big]
+        half = ((b - a) // 2 + leaf - 1) // leaf * leaf
+        mid = torch.minimum(a + half, b - 1)
+        bounds = torch.sort(torch.cat([bounds, mid])).values
+    new_id = torch.empty(n, dtype=torch.int64, device=dev)
+    new_id[order] = torch.arange(n, device=dev)
+    return new_id
+
+
+TC_AGG_WIDTHS = (64, 128, 256)
+TC_AGG_MIN_NODES = 1 << 18        # below this the gather kernel is launch / L2 bound anyway and the plan is not worth building
+TC_AGG_REORDER_ABOVE = 3.2        # staged rows per output row above which a k-d relabelling is tried
+
+
+def aggregate_mean(graph: "CSRGraph", x):
+    """Mean aggregation over ``graph``: the tensor-core block kernel when the graph carries a usable plan and the rows
+    qualify (bf16, H in 64/128/256), the gather kernel otherwise.  Both are deterministic; they differ by the association
+    order of fp32 additions only."""
+    pl = graph.plan
+    if pl is not None and pl.usable and x.dtype == torch.bfloat16 and x.shape[1] in TC_AGG_WIDTHS:
+        return aggregate_tc(pl, graph.inv_deg, x, graph.num_edges)
+    return aggregate(graph.rowptr, graph.col, graph.inv_deg, x)
+
+
+@dataclass
+class InferenceGraph:
+    """Graph prepared for large-mesh inference: CSR (+ block plan) of the possibly RELABELLED nodes.
+    ``order[new] = old`` permutes input rows (``x.index_select(0, order)``), ``new_id[old] = new`` restores outputs."""
+
+    graph: CSRGraph
+    new_id: torch.Tensor | None = None
+    order: torch.Tensor | None = None
+    staged_rows_per_row_given: float | None = None
+    staged_rows_per_row: float | None = None
+
+
+_INF_CACHE: "OrderedDict[tuple, InferenceGraph]" = OrderedDict()
+
+
+def get_inference_graph(edge_index: torch.Tensor, num_nodes: int, pos: torch.Tensor | None = None, reorder: str = "auto") -> InferenceGraph:
+    """One-time preparation of a large static mesh for bf16 inference (BASELINE.json config 4): CSR, block plan for
+    ``dfw_sage_aggregate_tc`` and - ``reorder`` = 'auto' (when the given numbering stages more than
+    ``TC_AGG_REORDER_ABOVE`` rows per output row and coordinates are available), 'always' or 'never' - the k-d node
+    relabelling of ``locality_order``.  Cached per ``edge_index`` tensor.  Costs two 16-byte D2H reads (plan statistics)."""
+    key = _cache_key(edge_index, num_nodes) + (reorder, pos is not None)
+    ig = _INF_CACHE.get(key)
+    if ig is not None and ig.graph is not None and (ig.graph.edge_index is edge_index or ig.new_id is not None):
+        _INF_CACHE.move_to_end(key)
+        return ig
     g = get_graph(edge_index, num_nodes)
-    paths = {"gather": lambda: aggregate(g.rowptr, g.col, g.inv_deg, x)}
-    if x.dtype == torch.bfloat16 and x.shape[1] in (64, 128, 256):
+    if g.plan is None:
+        g.plan = build_agg_plan(g.rowptr, g.col, num_nodes)
+    ok = g.plan.check()
+    ig = InferenceGraph(g, None, None, g.plan.staged_rows_per_row, g.plan.staged_rows_per_row)
+    want = reorder == "always" or (reorder == "auto" and (not ok or g.plan.staged_rows_per_row > TC_AGG_REORDER_ABOVE))
+    if want and pos is not None and num_nodes > 128:
+        new_id = locality_order(pos, edge_index)
+        ei2 = new_id[edge_index]
+        rowptr, col, _, inv_deg, status = csr_build_raw(ei2, num_nodes, want_perm=False)
+        g2 = CSRGraph(ei2, int(num_nodes), int(ei2.shape[1]), rowptr, col, inv_deg, None, status)
+        g2.plan = build_agg_plan(rowptr, col, num_nodes)
+        if g2.plan.check() and (not ok or g2.plan.staged_rows_per_row < 0.9 * g.plan.staged_rows_per_row):
+            order = torch.empty_like(new_id)
+            order[new_id] = torch.arange(num_nodes, device=new_id.device)
+            ig = InferenceGraph(g2, new_id, order, g.plan.staged_rows_per_row, g2.plan.staged_rows_per_row)
+    _INF_CACHE[key] = ig
+    while len(_INF_CACHE) > 4:
+        _INF_CACHE.popitem(last=False)
+    return ig
+
+
+def cfg4_aggregation_paths(edge_index, num_nodes, pos, x):
+    """The aggregation paths bench.py times on BASELINE.json config 4: name -> (zero-argument callable running ONE mean
+    aggregation of ``x`` over the graph, info dict).  One-time graph preparation happens here, outside the callables."""
+    import time
+
+    g = get_graph(edge_index, num_nodes)
+    paths = {"gather": (lambda: aggregate(g.rowptr, g.col, g.inv_deg, x), {"what": "dfw_sage_aggregate on the CSR in the given numbering"})}
+    if x.dtype == torch.bfloat16 and x.shape[1] in TC_AGG_WIDTHS:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         plan = build_agg_plan(g.rowptr, g.col, num_nodes)
-        if plan.check():
-            paths["tensor_core_blocks"] = lambda: aggregate_tc(plan, g.inv_deg, x, g.num_edges)
+        ok = plan.check()
+        t_plan = time.perf_counter() - t0
+        if ok:
+            paths["tensor_core_blocks"] = (lambda: aggregate_tc(plan, g.inv_deg, x, g.num_edges),
+                                           {"what": "dfw_sage_aggregate_tc, given numbering", "staged_rows_per_row": round(plan.staged_rows_per_row, 3),
+                                            "one_time_plan_ms": round(t_plan * 1e3, 2)})
+        g.plan = plan
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ig = get_inference_graph(edge_index, num_nodes, pos=pos, reorder="auto")
+        torch.cuda.synchronize()
+        t_prep = time.perf_counter() - t0
+        if ig.order is not None:
+            xp = x.index_select(0, ig.order)  # in the model the permutation is applied to the 10-wide input, not per layer
+            g2 = ig.graph
+            paths["tensor_core_blocks_kd_order"] = (
+                lambda: aggregate_tc(g2.plan, g2.inv_deg, xp, g2.num_edges),
+                {"what": "dfw_sage_aggregate_tc after the one-time k-d relabelling of the nodes (ops.locality_order, device)",
+                 "staged_rows_per_row": round(ig.staged_rows_per_row, 3), "staged_rows_per_row_given_numbering": round(ig.staged_rows_per_row_given, 3),
+                 "one_time_relabel_csr_plan_ms": round(t_prep * 1e3, 2)})
     return paths
 
 

@@ -113,3 +113,38 @@ def test_aggregate_tc_rejects_what_it_cannot_take(ops):
     gh = ops.get_graph(torch.from_numpy(hub).cuda(), n)
     ph = ops.build_agg_plan(gh.rowptr, gh.col, n)
     assert not ph.check()
+
+
+def test_large_mesh_inference_path_relabels_nodes_and_matches_the_plain_path(ops, monkeypatch):
+    """GraphSAGEModel bf16 inference on a randomly numbered tet mesh: the block plan + k-d relabelling path (input rows
+    permuted once, output restored) must give the plain path's predictions in the CALLER's node order."""
+    from deep_fem_uav_wing.gnn import synth
+    from deep_fem_uav_wing.gnn.model import GraphSAGEModel
+
+    mesh = synth.tet_lattice_wing(120000, seed=3, node_order="random")
+    n = mesh["num_nodes"]
+    x, ei = torch.from_numpy(mesh["x"]).cuda(), torch.from_numpy(mesh["edge_index"]).cuda()
+    torch.manual_seed(5)
+    model = GraphSAGEModel(10, 128, 1, 2, dropout=0.0).cuda().eval().set_compute_dtype(torch.bfloat16)
+    monkeypatch.setattr(ops, "TC_AGG_MIN_NODES", 1000)
+    k0 = ops.LAUNCH_COUNTER["kernels"]
+    with torch.no_grad():
+        out_plan = model(x, ei)
+    ig = ops.get_inference_graph(ei, n, pos=x[:, :3], reorder="auto")
+    assert ig.order is not None and ig.graph.plan.usable
+    assert ig.staged_rows_per_row_given > 8 and ig.staged_rows_per_row < 4.5  # random numbering -> compact blocks
+    assert torch.equal(torch.sort(ig.new_id).values, torch.arange(n, device="cuda"))
+    record("kd_relabel_random_tet_120k", staged_given=ig.staged_rows_per_row_given, staged_kd=ig.staged_rows_per_row)
+    monkeypatch.setattr(ops, "TC_AGG_MIN_NODES", 10 ** 12)
+    with torch.no_grad():
+        out_plain = model(x, ei)
+    assert out_plan.shape == out_plain.shape == (n, 1)
+    err = rel_max(out_plan.float().cpu(), out_plain.float().cpu())
+    record("large_mesh_inference_path_vs_plain", rel_max=err)
+    assert err < TOL_BF16
+    # 'never': plan in the given numbering, no permutation
+    monkeypatch.setattr(ops, "TC_AGG_MIN_NODES", 1000)
+    model.node_reorder = "never"
+    with torch.no_grad():
+        out_never = model(x, ei)
+    assert rel_max(out_never.float().cpu(), out_plain.float().cpu()) < TOL_BF16
