@@ -45,7 +45,7 @@ using namespace tc;
 
 constexpr int kBlockRows = 128;
 constexpr int kChunk = 64;        // staged source rows (K) per pipeline stage
-constexpr int kRecU16 = 136;      // uint16 per block record: row offsets [0..128], S at [129]; 272 B
+constexpr int kRecU16 = 136;      // uint16 per block record: S, #entries, chunk pointers [2 .. 2 + nchunks]; 272 B
 constexpr int kPlanCap = 3072;    // edges per block the plan (and the kernel's slot buffer) can hold: mean degree <= 24
 constexpr int kSortCap = 4096;    // power of two >= kPlanCap (bitonic sort in the plan build)
 constexpr int kIdxRing = 8;
@@ -55,12 +55,13 @@ constexpr int kMaxStages = 4;
 constexpr int kStagingBoxes = 1;  // shared memory goes to the pipeline (bytes in flight bound this kernel), not to the epilogue
 
 struct Params {
-    const int4* blk_meta;      // [nblocks] {src_off, S, slot_off, ne}
+    const int4* blk_meta;      // [nblocks] {src_off, S, slot_off, number of adjacency entries}
     const int32_t* plan_src;   // block b: plan_src[src_off .. src_off + round_up(max(S,1), 64))
     const uint16_t* plan_rec;  // [nblocks][kRecU16]
-    const uint16_t* plan_slot; // block b: plan_slot[slot_off .. slot_off + ne)
+    const uint16_t* plan_slot; // block b: adjacency entries plan_slot[slot_off .. slot_off + nent), ordered by chunk
     const float* row_scale;    // fp32 [N] or NULL
     const uint8_t* x;          // bf16 [N, H]
+    uint8_t* out;              // bf16 [N, H]
     int64_t N;
     int nblocks;
     int H;
@@ -103,8 +104,31 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ int chunks_of(int S) { return (max(S, 1) + kChunk - 1) / kChunk; }
+// mbarrier wait whose try_wait carries a suspend-time hint: the warp sleeps in hardware until the phase completes (or the
+// hint expires) instead of spinning through issue slots - 16 of this kernel's 20 warps are waiting at any time, and the
+// plain spin loop took half of all issue cycles (ncu r02c: 24 M + 19 M loop iterations per launch).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(20000u)
+            : "memory");
+        if (!ok && ++spins > (1u << 22)) {
+            printf("dfw_aggregate_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+            __trap();
+        }
+    } while (!ok);
+}
+#define mbar_wait mbar_wait_sleep
 
-__global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_constant__ CUtensorMap map_out, const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const Layout L = carve(p.H, p.stages);
@@ -126,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full[s], kProducerWarps + 4);
+            mbar_init(&full[s], kProducerWarps * 32 + 4);  // every producer lane (cp.async completion) + the adjacency warps
             mbar_init(&empty[s], 1);
         }
         for (int r = 0; r < kIdxRing; ++r) {
@@ -140,7 +164,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
             mbar_init(&acc_empty[b], 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        prefetch_tmap(&map_out);
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(tmem_cols) : "memory");
@@ -220,14 +243,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================== epilogue =====================
+        // Each warp owns TMEM lanes / block rows q*32 .. q*32+31 end to end: thread-per-row TMEM loads, a PRIVATE 4 KB slice
+        // of the staging box (swizzled, conflict-free), then the warp writes the rows back out with fully coalesced
+        // 16-byte stores (8 lanes = one 128-byte segment of one row).  No TMA store, no cross-warp barrier: the first version
+        // pushed every [128 rows x 128 B] box through cp.async.bulk.tensor stores and spent ~12 us per block in the
+        // epilogue (ncu r02c) - a box is 128 separate 128-byte row writes for the TMA unit.
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        const int et = threadIdx.x - 128;
-        uint8_t* stg = smem + L.staging;
-        int n_store = 0;
+        uint8_t* box = smem + L.staging;
+        const uint32_t row_bytes = (uint32_t)H * 2u;
         for (int i = 0; i < nmine; ++i) {
             const int b = (int)blockIdx.x + i * (int)gridDim.x;
-            const int64_t row = (int64_t)b * kBlockRows + m;
+            const int64_t row0 = (int64_t)b * kBlockRows;
+            const int64_t row = row0 + m;
             const float rs = (row < p.N) ? (p.row_scale ? __ldg(p.row_scale + row) : 1.f) : 0.f;
             const int ab = i & 1;
             mbar_wait(&acc_full[ab], (uint32_t)((i >> 1) & 1));
@@ -237,10 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
             tmem_ld32_issue(t_row, ra);
             for (int cb = 0; cb < H / 64; ++cb) {
                 tmem_ld32_issue(t_row + cb * 64 + 32, rb);
-                // the store that last used this staging box must have finished reading it
-                if (et == 0) tma_store_wait_read<kStagingBoxes - 1>();
-                epi_bar();
-                uint8_t* box = stg + (size_t)(n_store % kStagingBoxes) * (kBlockRows * 128);
+                __syncwarp();  // the read-back of the previous box is done
                 tmem_ld_wait(ra);
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
@@ -262,20 +287,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
                     u.from_float(f);
                     *reinterpret_cast<uint4*>(box + box_off(m, 4 + g4)) = u.v;
                 }
-                fence_proxy_async();
-                epi_bar();
-                if (et == 0) {
-                    tma_store_2d(&map_out, box, cb * 64, b * kBlockRows);
-                    tma_store_commit();
+                __syncwarp();
+                uint8_t* orow = p.out + (size_t)cb * 128 + (size_t)(lane & 7) * 16;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = q * 32 + it * 4 + (lane >> 3);
+                    const uint4 v = *reinterpret_cast<const uint4*>(box + box_off(r, lane & 7));
+                    if (row0 + r < p.N) *reinterpret_cast<uint4*>(orow + (size_t)(row0 + r) * row_bytes) = v;
                 }
-                ++n_store;
             }
             fence_tc_before();
             mbar_arrive(&acc_empty[ab]);
         }
-        if (et == 0) tma_store_wait_read<0>();
     } else if (warp >= 8 && warp < 12) {
-        // ===================== adjacency builder: thread m owns row m of the block =====================
+        // ===================== adjacency builder =====================
+        // Per chunk: every thread clears its own 128-byte line of the ADJ tile, the four warps meet at a named barrier, then
+        // the chunk's plan entries (one per distinct (source, row) pair, already ordered by chunk) are applied flat, one
+        // 2-byte store each - no per-row walk, no divergence.  (The first version let thread m walk row m's slots with
+        // data-dependent loops: ~900 clk per chunk, the bottleneck of the whole kernel - ncu r02e.)
         const int m = threadIdx.x - 256;
         int stage = 0;
         uint32_t phase = 0;
@@ -284,26 +313,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
             mbar_wait(&blk_full[bb], (uint32_t)((i >> 1) & 1));
             const uint8_t* buf = smem + L.blkbuf + (size_t)bb * L.blkbuf_bytes;
             const uint16_t* rec = reinterpret_cast<const uint16_t*>(buf);
-            const uint16_t* slots = reinterpret_cast<const uint16_t*>(buf + 288);
-            const int nch = chunks_of((int)rec[129]);
-            int e = rec[m];
-            const int e_end = rec[m + 1];
+            const uint16_t* ent = reinterpret_cast<const uint16_t*>(buf + 288);
+            const int nch = chunks_of((int)rec[0]);
             for (int c = 0; c < nch; ++c) {
                 mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* line = smem + (size_t)stage * L.stage + L.b_bytes + (size_t)m * 128;
+                uint8_t* tile = smem + (size_t)stage * L.stage + L.b_bytes;
+                uint8_t* line = tile + (size_t)m * 128;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)  // staggered so that the 8 lanes of a quarter-warp hit 8 different bank groups
                     *reinterpret_cast<uint4*>(line + ((j ^ (m & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-                const int lim = (c + 1) * kChunk;
-                while (e < e_end) {
-                    const int s = slots[e];
-                    if (s >= lim) break;
-                    int cnt = 1;
-                    ++e;
-                    while (e < e_end && slots[e] == s) { ++cnt; ++e; }  // duplicate edges count with multiplicity
-                    const int kk = s - c * kChunk;
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                const int t_end = rec[3 + c];
+                for (int t = (int)rec[2 + c] + m; t < t_end; t += 128) {
+                    const uint32_t e = ent[t];
+                    const uint32_t kk = e & 63u, row = (e >> 6) & 127u, cnt = (e >> 13) + 1u;
                     const __nv_bfloat16 v = __float2bfloat16_rn((float)cnt);
-                    *reinterpret_cast<__nv_bfloat16*>(line + ((((kk >> 3) ^ (m & 7))) << 4) + (kk & 7) * 2) = v;
+                    *reinterpret_cast<__nv_bfloat16*>(tile + row * 128u + (((kk >> 3) ^ (row & 7u)) << 4) + (kk & 7u) * 2u) = v;
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -323,13 +348,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
         const uint32_t dcol = (uint32_t)(c16 >> 3) * (kChunk * 128u);  // feature box
         const uint32_t row_bytes = (uint32_t)H * 2u;
         const uint8_t* xl = p.x + (size_t)c16 * 16;
-        int prev_stage = -1;
+        int stage = 0;
+        uint32_t phase = 0;
         for (int g = 0;; ++g) {
-            const int r = g % kIdxRing;
+            const int r = g & (kIdxRing - 1);
             mbar_wait(&idx_full[r], (uint32_t)((g / kIdxRing) & 1));
             if (idx_flag[r] == 0u) break;
-            const int stage = g % p.stages;
-            mbar_wait(&empty[stage], (uint32_t)(((g / p.stages) & 1) ^ 1));
+            mbar_wait(&empty[stage], phase ^ 1);
             const int32_t* idx = reinterpret_cast<const int32_t*>(smem + L.idx + (size_t)r * kChunk * 4);
             const uint32_t sb = smem_u32(smem + (size_t)stage * L.stage) + dcol;
             for (int it = 0; it < 8 / rpi; ++it) {
@@ -337,22 +362,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_const
                 const int src = idx[k];
                 cp_async16(sb + (uint32_t)k * 128u + (uint32_t)(((c16 & 7) ^ (k & 7)) << 4), xl + (size_t)src * row_bytes);
             }
-            cp_async_commit();
+            // completion is signalled by the copy engine itself: every lane's arrive fires when ITS copies of this chunk have
+            // landed (.noinc: it counts as one of the expected arrivals), so the warp never waits for data and all `stages`
+            // chunks can be in flight.  (A first version waited with cp.async.wait_group 1 before arriving: at most two chunks
+            // in flight whatever the stage count, ~1 us per chunk = the load latency / 2.)
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&idx_empty[r]);
-            if (prev_stage >= 0) {
-                cp_async_wait<1>();  // the previous chunk's rows have landed
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[prev_stage]);
-            }
-            prev_stage = stage;
-        }
-        if (prev_stage >= 0) {
-            cp_async_wait<0>();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[prev_stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     }
 
@@ -406,13 +423,19 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
         __syncthreads();
     }
 }
-// one CTA per block: sort the block's edges by source, number the distinct sources, emit list + slots + record
+// one CTA per block: sort the block's edges by (source, row), number the distinct sources, emit the source list, the
+// chunk-sorted adjacency entries and the record
+//   plan_src  : ascending distinct sources, padded to a multiple of 64 with the last one (finite rows under zero ADJ columns)
+//   plan_slot : one uint16 ENTRY per distinct (source, row) pair, ordered by (slot, row):  (count-1) << 13 | row << 6 | slot % 64
+//               - exactly the stores the kernel's adjacency warps perform, chunk c = entries [cptr[c], cptr[c+1])
+//   plan_rec  : [0] = S, [1] = number of entries, [2 .. 2 + nchunks] = cptr
 __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int4* __restrict__ meta,
                                                      int32_t* __restrict__ plan_src, uint16_t* __restrict__ plan_rec, uint16_t* __restrict__ plan_slot,
                                                      unsigned long long* __restrict__ status /*[0] max edges of a block, [1] sum of S*/) {
     __shared__ unsigned long long key[kSortCap];
-    __shared__ int wsum[8];
-    __shared__ int s_total;
+    __shared__ uint16_t rowoff[kBlockRows + 1];
+    __shared__ int wsum[2][8];
+    __shared__ int s_total[2];
     const int b = blockIdx.x;
     const int64_t r0 = (int64_t)b * kBlockRows;
     const int nr = (int)min((int64_t)kBlockRows, N - r0);
@@ -431,7 +454,8 @@ __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ 
         return;
     }
     if (threadIdx.x == 0) atomicMax(status, (unsigned long long)ne);
-    for (int t = threadIdx.x; t <= kBlockRows; t += 256) rec[t] = (uint16_t)(rowptr[r0 + min(t, nr)] - e0);
+    for (int t = threadIdx.x; t <= kBlockRows; t += 256) rowoff[t] = (uint16_t)(rowptr[r0 + min(t, nr)] - e0);
+    for (int t = threadIdx.x; t < kRecU16; t += 256) rec[t] = 0;
     int P = 2;
     while (P < ne) P <<= 1;
     for (int t = threadIdx.x; t < P; t += 256)
@@ -450,42 +474,64 @@ __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ 
             __syncthreads();
         }
     }
-    // heads of runs of equal sources -> slot numbers (each thread scans a contiguous piece)
+    // local edge index -> row of the block (the sort key's low half keeps CSR order, so equal sources come row by row)
+    auto row_of = [&](int idx) {
+        int lo = 0, hi = kBlockRows;  // largest r with rowoff[r] <= idx
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)rowoff[mid] <= idx) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
+    auto src_head = [&](int t) { return t == 0 || (key[t] >> 16) != (key[t - 1] >> 16); };
+    auto ent_head = [&](int t) { return src_head(t) || row_of((int)(key[t] & 0xffffu)) != row_of((int)(key[t - 1] & 0xffffu)); };
+    // two exclusive scans in one pass: distinct sources (slot numbers) and distinct (source, row) pairs (entry positions)
     const int per = (P + 255) / 256;
     const int t0 = threadIdx.x * per, t1 = min(t0 + per, ne);
-    int local = 0;
-    for (int t = t0; t < t1; ++t) local += (t == 0 || (key[t] >> 16) != (key[t - 1] >> 16)) ? 1 : 0;
+    int local[2] = {0, 0};
+    for (int t = t0; t < t1; ++t) {
+        local[0] += src_head(t) ? 1 : 0;
+        local[1] += ent_head(t) ? 1 : 0;
+    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = local;
+    int inc[2] = {local[0], local[1]};
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
+        const int v0 = __shfl_up_sync(0xffffffffu, inc[0], o), v1 = __shfl_up_sync(0xffffffffu, inc[1], o);
+        if (lane >= o) { inc[0] += v0; inc[1] += v1; }
     }
-    if (lane == 31) wsum[wid] = inc;
+    if (lane == 31) { wsum[0][wid] = inc[0]; wsum[1][wid] = inc[1]; }
     __syncthreads();
-    int off = inc - local;
-    for (int w = 0; w < wid; ++w) off += wsum[w];
-    if (threadIdx.x == 255) s_total = off + local;
-    int slot = off - 1;
+    int off[2] = {inc[0] - local[0], inc[1] - local[1]};
+    for (int w = 0; w < wid; ++w) { off[0] += wsum[0][w]; off[1] += wsum[1][w]; }
+    if (threadIdx.x == 255) { s_total[0] = off[0] + local[0]; s_total[1] = off[1] + local[1]; }
+    int slot = off[0] - 1, epos = off[1] - 1;
     for (int t = t0; t < t1; ++t) {
-        const bool head = (t == 0 || (key[t] >> 16) != (key[t - 1] >> 16));
-        if (head) {
+        if (src_head(t)) {
             ++slot;
             plan_src[(size_t)mm.x + slot] = (int32_t)(key[t] >> 16);
         }
-        plan_slot[(size_t)mm.z + (int)(key[t] & 0xffffu)] = (uint16_t)slot;
+        if (ent_head(t)) {
+            ++epos;
+            const int row = row_of((int)(key[t] & 0xffffu));
+            int cnt = 1;  // multiplicity of a duplicate edge: the run of equal (source, row) may continue into the next thread's piece
+            for (int u = t + 1; u < ne && !ent_head(u); ++u) ++cnt;
+            if (cnt > 8) atomicMax(status, 1ull << 40);  // more than the 3-bit field holds: the plan is unusable
+            plan_slot[(size_t)mm.z + epos] = (uint16_t)((min(cnt, 8) - 1) << 13 | row << 6 | (slot & (kChunk - 1)));
+            if (src_head(t) && (slot & (kChunk - 1)) == 0) rec[2 + slot / kChunk] = (uint16_t)epos;  // first entry of chunk slot / 64
+        }
     }
     __syncthreads();
-    const int S = s_total;
+    const int S = s_total[0], nent = s_total[1];
     const int padded = (max(S, 1) + kChunk - 1) / kChunk * kChunk;
-    const int32_t fill = S > 0 ? (int32_t)(key[ne - 1] >> 16) : 0;  // replicate the last source: finite rows, zero ADJ columns
+    const int32_t fill = S > 0 ? (int32_t)(key[ne - 1] >> 16) : 0;
     for (int t = S + threadIdx.x; t < padded; t += 256) plan_src[(size_t)mm.x + t] = fill;
     if (threadIdx.x == 0) {
-        rec[129] = (uint16_t)S;
-        for (int t = 130; t < kRecU16; ++t) rec[t] = 0;
+        rec[0] = (uint16_t)S;
+        rec[1] = (uint16_t)nent;
+        rec[2 + padded / kChunk] = (uint16_t)nent;  // cptr[nchunks] (an empty block has one all-zero chunk: cptr = {0, 0})
         mm.y = S;
-        mm.w = ne;
+        mm.w = nent;
         meta[b] = mm;
         atomicAdd(status + 1, (unsigned long long)S);
     }
@@ -555,13 +601,11 @@ extern "C" int dfw_sage_aggregate_tc(const int32_t* blk_meta, const int32_t* pla
     while (stages > 2 && carve((int)H, stages).total + 1024 > 227 * 1024) --stages;
     p.stages = stages;
     const size_t smem = carve((int)H, stages).total + 1024;
-    CUtensorMap map;
-    memset(&map, 0, sizeof(map));
-    if (tc::make_map(&map, out, N, H, 2, kBlockRows)) return 1;
+    p.out = static_cast<uint8_t*>(out);
     auto kern = k_aggregate_tc;
     DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)std::min<int64_t>(nb, kNumSMs);
-    kern<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(map, p);
+    kern<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     DFW_LAUNCH_CHECK();
     return 0;
 }

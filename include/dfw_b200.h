@@ -124,14 +124,16 @@ int dfw_sage_aggregate_scaled(const int32_t* rowptr, const int32_t* col, const f
  * (b') the same mean / sum aggregation for bf16 rows on the tensor cores (block-sparse product; refined meshes, BASELINE.json
  *     config 4).  Replaces the same PyG expression as dfw_sage_aggregate (index_select + scatter_add_ + divide behind
  *     SAGEConv(aggr='mean'), call site model.py:90).  Rows are cut into blocks of 128 consecutive rows; a one-time PLAN of the
- *     CSR lists per block its distinct source rows and a 16-bit slot per edge; per block  OUT[128,H] = ADJ[128,S] . X[S,H]
+ *     CSR lists per block its distinct source rows (plan_src, padded to multiples of 64) and one 16-bit entry per distinct
+ *     (source, row) pair - (multiplicity-1) << 13 | row << 6 | slot % 64, ordered by 64-source chunk (plan_slot) - with the
+ *     chunk pointers in the block record (plan_rec: S, #entries, cptr[...]); per block  OUT[128,H] = ADJ[128,S] . X[S,H]
  *     runs as tcgen05.mma with fp32 accumulation (ADJ = edge multiplicities: exact products), row_scale in the epilogue.
  *     Result = the CSR-order fp32 sum up to the association order of the fp32 additions (<= 1 bf16 ulp after rounding).
  *
  *     dfw_agg_plan_sizes: array lengths for a graph of N rows / E edges: blk_meta int32 [4*nblocks], plan_src int32 [src_cap],
  *       plan_rec uint16 [136*nblocks], plan_slot uint16 [slot_cap]; ws of dfw_agg_plan_build: 8 bytes per block.
  *     dfw_agg_plan_build: status uint64 [2] (device): [0] = largest number of edges in a block - the plan is USABLE only if
- *       it is <= dfw_agg_plan_max_block_edges(); [1] = total number of staged rows (sum of S over the blocks: the locality
+ *       it is <= dfw_agg_plan_max_block_edges() (an edge repeated more than 8 times also pushes it above); [1] = total number of staged rows (sum of S over the blocks: the locality
  *       measure, staged rows per output row = [1] / N).  No host synchronisation.
  *     dfw_sage_aggregate_tc: x, out bf16 [N,H], H in {64,128,256}; row_scale fp32 [N] (inv_deg: mean) or NULL (sum).
  * ---------------------------------------------------------------------------------------- */

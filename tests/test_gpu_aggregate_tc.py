@@ -55,16 +55,22 @@ def test_block_plan_matches_design_oracle(ops, name):
     assert meta.shape[0] >= nb
     total = 0
     for b in range(nb):
-        s_off, S, t_off, ne = (int(v) for v in meta[b])
+        s_off, S, t_off, nent = (int(v) for v in meta[b])
         r0, r1 = 128 * b, min(128 * b + 128, n)
         e0, e1 = int(rowptr[r0]), int(rowptr[r1])
-        assert ne == e1 - e0 and S == blk_ptr[b + 1] - blk_ptr[b] and s_off % 64 == 0 and t_off % 8 == 0
+        assert S == blk_ptr[b + 1] - blk_ptr[b] and s_off % 64 == 0 and t_off % 8 == 0
         assert np.array_equal(src[s_off:s_off + S], blk_src[blk_ptr[b]:blk_ptr[b + 1]])  # ascending distinct sources
         pad = (max(S, 1) + 63) // 64 * 64
         assert np.all(src[s_off + S:s_off + pad] == (src[s_off + S - 1] if S else 0))
-        assert np.array_equal(slots[t_off:t_off + ne], slot[e0:e1])
-        want_off = np.minimum(rowptr[r0:r0 + 129] if r0 + 129 <= n + 1 else np.concatenate([rowptr[r0:n + 1], np.full(r0 + 129 - n - 1, e1)]), e1) - e0
-        assert np.array_equal(rec[b, :129], want_off.astype(np.uint16)) and rec[b, 129] == S
+        # adjacency entries: one per distinct (slot, row) pair with its multiplicity, ordered by (slot, row)
+        rows_of_edges = np.repeat(np.arange(r1 - r0), np.diff(rowptr[r0:r1 + 1]))
+        pairs, counts = np.unique(np.stack([slot[e0:e1].astype(np.int64), rows_of_edges]), axis=1, return_counts=True)
+        want = ((counts - 1) << 13 | pairs[1] << 6 | (pairs[0] & 63)).astype(np.uint16)
+        assert nent == want.size and rec[b, 0] == S and rec[b, 1] == nent
+        assert np.array_equal(slots[t_off:t_off + nent], want)
+        nch = pad // 64
+        cptr = np.searchsorted(pairs[0], 64 * np.arange(nch + 1)) if nent else np.zeros(nch + 1, dtype=np.int64)
+        assert np.array_equal(rec[b, 2:3 + nch], cptr.astype(np.uint16))
         total += S
     assert abs(plan.staged_rows_per_row * n - total) < 0.5
 
@@ -113,6 +119,16 @@ def test_aggregate_tc_rejects_what_it_cannot_take(ops):
     gh = ops.get_graph(torch.from_numpy(hub).cuda(), n)
     ph = ops.build_agg_plan(gh.rowptr, gh.col, n)
     assert not ph.check()
+    # so is an edge repeated more often than the 3-bit multiplicity field holds
+    rep = np.stack([np.zeros(9, dtype=np.int64), np.ones(9, dtype=np.int64)])
+    gr = ops.get_graph(torch.from_numpy(rep).cuda(), 2)
+    assert not ops.build_agg_plan(gr.rowptr, gr.col, 2).check()
+    rep8 = rep[:, :8].copy()
+    g8 = ops.get_graph(torch.from_numpy(rep8).cuda(), 2)
+    p8 = ops.build_agg_plan(g8.rowptr, g8.col, 2)
+    assert p8.check()
+    out8 = ops.aggregate_tc(p8, None, torch.ones(2, 64, device="cuda", dtype=torch.bfloat16))
+    assert out8[1].float().eq(8).all() and out8[0].float().eq(0).all()
 
 
 def test_large_mesh_inference_path_relabels_nodes_and_matches_the_plain_path(ops, monkeypatch):
