@@ -81,7 +81,7 @@ class GraphedTrainStep:
         # the CSR (and its transpose) is built - or fetched from the cache - BEFORE the capture and handed to the model as an
         # object: the CUDA graph holds raw pointers into it, so it must stay alive with the replay closure whatever the
         # LRU cache of ops.get_graph evicts later
-        csr = ops.get_graph(edge_index, int(x.shape[0]))
+        csr = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, int(x.shape[0]))
         csr.transpose()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
