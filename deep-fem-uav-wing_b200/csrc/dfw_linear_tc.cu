@@ -43,7 +43,7 @@ struct Maps {
     CUtensorMap a[2];
     CUtensorMap w_hi[2];
     CUtensorMap w_lo[2];
-    CUtensorMap out, pre, res;  // [N, Hout] tensors of the epilogue, boxes of [128 rows x 128 B]
+    CUtensorMap res;  // the residual [N, Hout] tensor, boxes of [128 rows x 128 B]
 };
 
 
@@ -166,8 +166,6 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
             prefetch_tmap(&maps.a[1]);
             prefetch_tmap(&maps.w_hi[1]);
         }
-        if (p.out) prefetch_tmap(&maps.out);
-        if (p.pre_out) prefetch_tmap(&maps.pre);
         if (p.residual) prefetch_tmap(&maps.res);
     }
     if (warp == 2) {
@@ -309,7 +307,6 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
         const float4* bet4 = reinterpret_cast<const float4*>(cvec + 512);
         const float4* rdw4 = reinterpret_cast<const float4*>(cvec + 768);
         uint8_t* stg = smem + L.staging;
-        int n_store = 0;  // TMA stores issued so far (staging buffer = n_store % nbuf)
         float mean = 0.f, rstd = 1.f;
 
         // y = (acc + bias) * row_scale for the 32 columns starting at c0
@@ -339,25 +336,26 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 }
             }
         };
+        // Output path: every epilogue warp owns tile rows q*32 .. q*32+31 end to end.  Its threads stage their rows in the
+        // warp's PRIVATE 4 KB slice of one swizzled [128 rows x 128 B] box (conflict-free), then the warp writes the slice out
+        // with coalesced 16-byte stores (8 lanes = one 128-byte segment of one row, 4 rows per instruction).  No TMA store, no
+        // proxy fence, no barrier between the epilogue warps.  (Round 1 pushed every box through cp.async.bulk.tensor stores:
+        // a [128 x 128 B] box is 128 separate row writes for the TMA unit and cost ~0.5 us of acquire / store per 32-column
+        // group on the tile's critical path, profiles/r01c_lin_fwd_fp32_ncu_summary.txt.)
+        const uint32_t out_row_bytes = (uint32_t)H * (uint32_t)sizeof(T);
         auto acquire_box = [&]() -> uint8_t* {
-            // the store that last used this buffer must have finished READING it
-            if (et == 0) {
-                if (L.nbuf >= 4) tma_store_wait_read<3>();
-                else if (L.nbuf == 3) tma_store_wait_read<2>();
-                else if (L.nbuf == 2) tma_store_wait_read<1>();
-                else tma_store_wait_read<0>();
-            }
-            epi_bar();
-            return stg + (size_t)(n_store % L.nbuf) * (kTileM * kChunkBytes);
+            __syncwarp();  // the read-back of this warp's slice for the previous box is done
+            return stg;
         };
-        auto release_box = [&](const CUtensorMap* map, uint8_t* box, int col0) {
-            fence_proxy_async();
-            epi_bar();
-            if (et == 0) {
-                tma_store_2d(map, box, col0, (int)m_base);
-                tma_store_commit();
+        auto release_box = [&](void* gbase, uint8_t* box, int col0) {
+            __syncwarp();
+            uint8_t* g = static_cast<uint8_t*>(gbase) + (size_t)col0 * sizeof(T) + (size_t)(lane & 7) * 16;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int r = q * 32 + it * 4 + (lane >> 3);
+                const uint4 v = *reinterpret_cast<const uint4*>(box + box_off(r, lane & 7));
+                if (m_base + r < p.N) *reinterpret_cast<uint4*>(g + (size_t)(m_base + r) * out_row_bytes) = v;
             }
-            ++n_store;
         };
         // Every pass walks the row 32 columns at a time with the TMEM load of the NEXT group in flight while the
         // current one is worked on (the values are copied out of the load's registers first, so one register set per
@@ -405,7 +403,7 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                 if (p.pre_out) {
                     if (c0 % EPC == 0) box = acquire_box();  // as late as possible: the store that used this buffer has had the whole group's math to finish reading it
                     stage_row(box, c0 % EPC, v);
-                    if ((c0 + 32) % EPC == 0) release_box(&maps.pre, box, c0 / EPC * EPC);
+                    if ((c0 + 32) % EPC == 0) release_box(p.pre_out, box, c0 / EPC * EPC);
                 }
             }
             tmem_st_wait();
@@ -527,14 +525,13 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
                     if (c0 % EPC == 0) box = acquire_box();
                     if (et == 0 && g < 4) PROBE(49 + 4 * g);  // box acquired
                     stage_row(box, h * 32, v);
-                    if ((c0 + 32) % EPC == 0) release_box(&maps.out, box, ob * EPC);
+                    if ((c0 + 32) % EPC == 0) release_box(p.out, box, ob * EPC);
                 }
                 if (et == 0 && g < 4) PROBE(52 + 4 * g);  // staged + store issued
             }
         }
         if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
         if (et == 0) PROBE(46);  // pass 3 done
-        if (et == 0) tma_store_wait_read<0>();  // smem must outlive the bulk stores' reads
         if (et == 0) PROBE(47);
     }
 
@@ -546,6 +543,378 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     }
     if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
     if (threadIdx.x == 0) PROBE(48);
+}
+
+// =====================================================================================================================
+// Persistent variant: one CTA per SM loops over 128-row tiles.
+//   * K chunks of 128 bytes (SWIZZLE_128B) for fp32 too: the TMA unit retires ~one box ROW per 2 clk whatever its width
+//     (tools/probes/tma_rate_probe.cu: the SAGE-layer operand stream takes 72 us with 64-byte rows, 40 us with 128-byte rows),
+//     so the 64-byte chunks that let two CTAs share an SM in k_linear_tc also capped its main loop.
+//   * the accumulator is double-buffered in TMEM (2 x (main + cross) x Npad columns <= 512): two epilogue warpgroups take
+//     alternate tiles, so a tile's three epilogue passes (~10 us) run under the main loops of the next TWO tiles, and no
+//     wave quantisation is left (1563 tiles on 296 CTA slots were 5.28 -> 6 rounds).
+//   * per-column constants are loaded once per CTA; outputs leave through per-warp staging slices and coalesced stores, the
+//     residual is read (coalesced) in the same write-back loop instead of being re-staged through shared memory.
+// Warps: 0 TMA producer, 1 MMA issuer, 2 TMEM owner, 4-7 / 8-11 epilogue warpgroups (even / odd tiles), 12-15 converters (fp32).
+// =====================================================================================================================
+constexpr int kPThreads = 512;
+constexpr int kPStagesMax = 4;
+
+struct PLayout {
+    uint32_t a_hi, a_lo, w_hi, w_lo, stage_bytes, staging, cvec, bars, total;
+};
+__host__ __device__ inline PLayout pcarve(bool tf32, int Npad, int Hout, int stages) {
+    PLayout L;
+    const uint32_t a = kTileM * 128u;                                    // 16 KB activation box
+    const uint32_t w = ((uint32_t)Npad * 128u + 1023u) / 1024u * 1024u;  // weight box of one 128-byte K chunk
+    L.a_hi = 0;
+    L.a_lo = a;
+    L.w_hi = tf32 ? 2 * a : a;
+    L.w_lo = L.w_hi + w;
+    L.stage_bytes = tf32 ? 2 * a + 2 * w : a + w;
+    L.staging = L.stage_bytes * (uint32_t)stages;    // 8 epilogue warps x [32 rows x 64 B]
+    L.cvec = L.staging + 8u * 2048u;
+    L.bars = L.cvec + 4u * (uint32_t)((Hout + 31) / 32 * 32) * 4u;
+    L.total = L.bars + 8u * (3 * kPStagesMax + 4) + 16u;
+    return L;
+}
+
+template <typename T, bool TF32>
+__global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_constant__ Maps maps, const Args p, const int num_tiles) {
+    constexpr int KPC = 128 / (int)sizeof(T);   // K elements per 128-byte chunk
+    constexpr int SCOLS = 64 / (int)sizeof(T);  // columns per 64-byte staging round: 16 fp32 / 32 bf16
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const PLayout L = pcarve(TF32, p.Npad, p.Hout, p.stages);
+    const int HP = (p.Hout + 31) / 32 * 32;
+    float* cvec = reinterpret_cast<float*>(smem + L.cvec);  // [4][HP]: bias, gamma, beta, rowdot_w
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* empty = full + kPStagesMax;
+    uint64_t* conv = empty + kPStagesMax;
+    uint64_t* acc_full = conv + kPStagesMax;   // [2]
+    uint64_t* acc_empty = acc_full + 2;        // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_chunks = p.chunks[0] + p.chunks[1];
+    const int nmine = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int regions = TF32 ? 2 : 1;
+    const uint32_t buf_cols = (uint32_t)(regions * p.Npad);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&conv[s], 4);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&maps.a[0]);
+        prefetch_tmap(&maps.w_hi[0]);
+        if (p.chunks[1]) {
+            prefetch_tmap(&maps.a[1]);
+            prefetch_tmap(&maps.w_hi[1]);
+        }
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int c = threadIdx.x; c < p.Hout; c += kPThreads) {
+        cvec[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+        cvec[HP + c] = p.gamma ? __ldg(p.gamma + c) : 1.f;
+        cvec[2 * HP + c] = p.beta ? __ldg(p.beta + c) : 0.f;
+        cvec[3 * HP + c] = p.rowdot_w ? __ldg(p.rowdot_w + c) : 0.f;
+    }
+    fence_tc_before();
+    __syncthreads();
+    fence_tc_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t stage_tx = (uint32_t)(kTileM * 128 + p.Npad * 128 * (TF32 ? 2 : 1));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nmine; ++i) {
+                const int m_base = ((int)blockIdx.x + i * (int)gridDim.x) * kTileM;
+                for (int c = 0; c < total_chunks; ++c) {
+                    const int seg = c >= p.chunks[0];
+                    const int kc = (seg ? c - p.chunks[0] : c) * KPC;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = smem + (size_t)stage * L.stage_bytes;
+                    mbar_arrive_expect_tx(&full[stage], stage_tx);
+                    tma_load_2d(st + L.a_hi, &maps.a[seg], &full[stage], kc, m_base);
+                    tma_load_2d(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0);
+                    if (TF32) tma_load_2d(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t fmt = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * p.Npad) >> 3) << 17);  // [w_hi | w_lo] in one instruction
+            const uint64_t dbase = make_desc_k<128>(0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nmine; ++i) {
+                const int ab = i & 1;
+                mbar_wait(&acc_empty[ab], (uint32_t)(((i >> 1) & 1) ^ 1));
+                fence_tc_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)ab * buf_cols;
+                uint32_t accumulate = 0;
+                for (int c = 0; c < total_chunks; ++c) {
+                    mbar_wait(TF32 ? &conv[stage] : &full[stage], phase);
+                    fence_tc_after();
+                    const uint32_t st = smem_u32(smem + (size_t)stage * L.stage_bytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // UMMA_K = 32 bytes
+                        const uint64_t a_hi = dbase + ((st + L.a_hi + k * 32) >> 4);
+                        const uint64_t w_hi = dbase + ((st + L.w_hi + k * 32) >> 4);
+                        if (TF32) {
+                            const uint64_t a_lo = dbase + ((st + L.a_lo + k * 32) >> 4);
+                            umma<TF32>(d_tmem, a_hi, w_hi, idesc2, accumulate);                   // main = a_hi.w_hi | cross = a_hi.w_lo
+                            umma<TF32>(d_tmem + (uint32_t)p.Npad, a_lo, w_hi, idesc, 1u);         // cross += a_lo.w_hi
+                        } else {
+                            umma<TF32>(d_tmem, a_hi, w_hi, idesc, accumulate);
+                        }
+                        accumulate = 1u;
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[ab]);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== converters (fp32): a_lo = a - trunc_tf32(a), in place beside the TMA tile =====
+        if (TF32) {
+            const int ct = threadIdx.x - 384;
+            int stage = 0;
+            uint32_t phase = 0;
+            const int nchunks = nmine * total_chunks;
+            for (int g = 0; g < nchunks; ++g) {
+                mbar_wait(&full[stage], phase);
+                uint8_t* st = smem + (size_t)stage * L.stage_bytes;
+                const float4* hi = reinterpret_cast<const float4*>(st + L.a_hi);
+                float4* lo = reinterpret_cast<float4*>(st + L.a_lo);
+#pragma unroll
+                for (int j = 0; j < (kTileM * 128 / 16) / 128; ++j) lo[ct + j * 128] = tf32_lo(hi[ct + j * 128]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warpgroups: WG0 (warps 4-7) takes even tiles, WG1 (warps 8-11) odd tiles =====
+        const int wg = (warp - 4) >> 2;
+        const int q = warp & 3;  // TMEM lane quarter
+        const int r_in_tile = q * 32 + lane;
+        const int H = p.Hout;
+        const int n32 = H / 32;
+        const bool ln = p.flags & DFW_EP_LAYERNORM, relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
+        const uint64_t seed = drop ? resolve_seed(p.seed, p.flags) : 0ull;
+        const float4* bias4 = reinterpret_cast<const float4*>(cvec);
+        const float4* gam4 = reinterpret_cast<const float4*>(cvec + HP);
+        const float4* bet4 = reinterpret_cast<const float4*>(cvec + 2 * HP);
+        const float4* rdw4 = reinterpret_cast<const float4*>(cvec + 3 * HP);
+        uint8_t* slice = smem + L.staging + (size_t)(warp - 4) * 2048;  // this warp's [32 rows x 64 B]
+        const uint32_t row_bytes = (uint32_t)H * (uint32_t)sizeof(T);
+        const bool y_in_tmem = ln || p.pre_out;
+
+        for (int i = wg; i < nmine; i += 2) {
+            const int64_t m_base = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * kTileM;
+            const int64_t row = m_base + r_in_tile;
+            const bool rok = row < p.N;
+            const int ab = i & 1;
+            const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
+            const uint32_t row_key = drop ? dropout_row_key(seed, (uint64_t)row) : 0u;
+            mbar_wait(&acc_full[ab], (uint32_t)((i >> 1) & 1));
+            fence_tc_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * buf_cols;
+
+            // one 64-byte piece per row of this warp's 32 rows -> global, coalesced (4 lanes = one row piece), + residual
+            auto write_out = [&](void* gbase, const void* rbase, int col0, const uint4 (&pk)[4]) {
+                __syncwarp();  // the previous round's read-back is done
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slice + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk[j];
+                __syncwarp();
+                const int jj = lane & 3;
+                const size_t coff = (size_t)col0 * sizeof(T) + (size_t)jj * 16;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int rr = it * 8 + (lane >> 2);
+                    uint4 v = *reinterpret_cast<const uint4*>(slice + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
+                    const int64_t grow = m_base + q * 32 + rr;
+                    if (grow < p.N) {
+                        const size_t off = (size_t)grow * row_bytes + coff;
+                        if (rbase) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(rbase) + off);
+                            if constexpr (sizeof(T) == 4) {
+                                v.x = __float_as_uint(__uint_as_float(v.x) + __uint_as_float(rv.x));
+                                v.y = __float_as_uint(__uint_as_float(v.y) + __uint_as_float(rv.y));
+                                v.z = __float_as_uint(__uint_as_float(v.z) + __uint_as_float(rv.z));
+                                v.w = __float_as_uint(__uint_as_float(v.w) + __uint_as_float(rv.w));
+                            } else {
+                                Vec16<T> a, b;
+                                a.v = v;
+                                b.v = rv;
+                                float fa[8], fb[8];
+                                a.to_float(fa);
+                                b.to_float(fb);
+#pragma unroll
+                                for (int e8 = 0; e8 < 8; ++e8) fa[e8] += fb[e8];
+                                a.from_float(fa);
+                                v = a.v;
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(static_cast<uint8_t*>(gbase) + off) = v;
+                    }
+                }
+            };
+            // 32 fp32 values of this thread's row (columns c0 .. c0+31) -> T -> global
+            auto emit32 = [&](void* gbase, const void* rbase, int c0, const float* v) {
+                if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            pk[j] = make_uint4(__float_as_uint(v[h * 16 + 4 * j]), __float_as_uint(v[h * 16 + 4 * j + 1]), __float_as_uint(v[h * 16 + 4 * j + 2]),
+                                               __float_as_uint(v[h * 16 + 4 * j + 3]));
+                        write_out(gbase, rbase, c0 + h * SCOLS, pk);
+                    }
+                } else {
+                    uint4 pk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        Vec16<T> u;
+                        u.from_float(v + 8 * j);
+                        pk[j] = u.v;
+                    }
+                    write_out(gbase, rbase, c0, pk);
+                }
+            };
+            // y = (acc + bias) * row_scale for the 32 columns starting at c0
+            auto finish_y = [&](int c0, float* v) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float4 b = bias4[c0 / 4 + g];
+                    v[4 * g] = (v[4 * g] + b.x) * rs;
+                    v[4 * g + 1] = (v[4 * g + 1] + b.y) * rs;
+                    v[4 * g + 2] = (v[4 * g + 2] + b.z) * rs;
+                    v[4 * g + 3] = (v[4 * g + 3] + b.w) * rs;
+                }
+            };
+            auto load_acc = [&](int c0, float* v) {  // hi*hi + cross terms, summed in round-to-nearest fp32 (see tmem_combine)
+                tmem_ld32(t_row + c0, v);
+                if (TF32) {
+                    float w[32];
+                    tmem_ld32(t_row + p.Npad + c0, w);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += w[j];
+                }
+            };
+            float mean = 0.f, rstd = 1.f;
+            // ---- pass 1: y written back to region 0, row sum, pre-activation tensor ----
+            if (y_in_tmem) {
+                float s = 0.f;
+                for (int g = 0; g < n32; ++g) {
+                    const int c0 = g * 32;
+                    float v[32];
+                    load_acc(c0, v);
+                    finish_y(c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s += v[j];
+                    tmem_st32_nowait(t_row + c0, v);
+                    if (p.pre_out) emit32(p.pre_out, nullptr, c0, v);
+                }
+                tmem_st_wait();
+                mean = s / (float)H;
+            }
+            // ---- pass 2: variance around the mean (two-pass, like torch) ----
+            if (ln) {
+                float qs = 0.f;
+                for (int g = 0; g < n32; ++g) {
+                    float v[32];
+                    tmem_ld32(t_row + g * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d = v[j] - mean;
+                        qs = fmaf(d, d, qs);
+                    }
+                }
+                rstd = rsqrtf(qs / (float)H + p.eps);
+                if (p.ln_stats && rok) {
+                    p.ln_stats[2 * row] = mean;
+                    p.ln_stats[2 * row + 1] = rstd;
+                }
+            }
+            // ---- pass 3: normalise, ReLU, dropout, row-dot, (+ residual in the write-back), store ----
+            float dot = 0.f;
+            for (int g = 0; g < n32; ++g) {
+                const int c0 = g * 32;
+                float v[32];
+                if (y_in_tmem) {
+                    tmem_ld32(t_row + c0, v);
+                } else {
+                    load_acc(c0, v);
+                    finish_y(c0, v);
+                }
+                if (ln) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 ga = gam4[c0 / 4 + g4], be = bet4[c0 / 4 + g4];
+                        v[4 * g4] = (v[4 * g4] - mean) * rstd * ga.x + be.x;
+                        v[4 * g4 + 1] = (v[4 * g4 + 1] - mean) * rstd * ga.y + be.y;
+                        v[4 * g4 + 2] = (v[4 * g4 + 2] - mean) * rstd * ga.z + be.z;
+                        v[4 * g4 + 3] = (v[4 * g4 + 3] - mean) * rstd * ga.w + be.w;
+                    }
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (drop) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t bits = dropout_bits(row_key, (uint32_t)(c0 + j));
+                        v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
+                    }
+                }
+                if (p.rowdot_out) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 w = rdw4[c0 / 4 + g4];
+                        dot = fmaf(v[4 * g4], w.x, dot);
+                        dot = fmaf(v[4 * g4 + 1], w.y, dot);
+                        dot = fmaf(v[4 * g4 + 2], w.z, dot);
+                        dot = fmaf(v[4 * g4 + 3], w.w, dot);
+                    }
+                }
+                if (p.out) emit32(p.out, p.residual, c0, v);
+            }
+            if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
+            fence_tc_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+    }
+
+    fence_tc_before();
+    __syncthreads();
+    if (warp == 2) {
+        fence_tc_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
 }
 
 // ---- weight preparation: (optional transpose) + TF32 hi/lo split, or plain copy/transpose for bf16 ----
@@ -695,6 +1064,56 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
         DFW_LAUNCH_CHECK();
     }
 
+    // ---- persistent variant (one CTA per SM, 128-byte K chunks, double-buffered accumulator) where its TMEM budget fits ----
+    {
+        // Measured A/B (tools/lin_ab.py, profiles/r02_linear_persistent_ab.json; us, classic -> persistent): single-operand
+        // linears (encoder / decoder / their input gradients) 72.7 -> 58.4 (fp32 H=128), 55.9 -> 41.7 (bf16 H=128), 550 -> 449
+        // (bf16 H=256, 2 M rows); H=64 layers 87 -> 83; but the two-operand SAGE shapes at H >= 128 lose 2-14 % (140 -> 146 fp32
+        // H=128, 1128 -> 1289 bf16 H=256): with K = 2H the 3 x 64 KB (fp32) stages keep only two chunks in flight and the main
+        // loop waits on TMA latency (ncu r02l: converters 11 % of samples waiting for data, epilogue warps idle on acc_full).
+        // Policy: persistent for single-operand calls and for Hout <= 64; DFW_TC_PERSIST=0 / 2 forces never / always.
+        static const int env_persist = [] { const char* e = getenv("DFW_TC_PERSIST"); return e ? atoi(e) : 1; }();
+        const int Npad = (int)((Hout + 15) / 16 * 16);
+        const int regions = tf32 ? 2 : 1;
+        const int64_t tiles64 = (args.N + kTileM - 1) / kTileM;
+        const bool want = env_persist == 2 || (env_persist == 1 && (!a2 || Npad <= 64));
+        if (want && 2 * regions * Npad <= 512 && Hout % 32 == 0 && tiles64 >= 2) {
+            Maps pm;
+            memset(&pm, 0, sizeof(pm));
+            args.Npad = Npad;
+            args.nacc = 1;
+            int cols = 32;
+            while (cols < 2 * regions * Npad) cols <<= 1;
+            args.tmem_cols = cols;
+            const void* as2[2] = {a1, a2};
+            for (int i = 0; i < (a2 ? 2 : 1); ++i) {
+                if (make_map(&pm.a[i], as2[i], args.N, ks[i], e, kTileM, kMapSw128)) return 1;
+                if (make_map(&pm.w_hi[i], wuse[i], Hout, ks[i], e, Npad, kMapSw128)) return 1;
+                if (tf32 && make_map(&pm.w_lo[i], lo[i], Hout, ks[i], e, Npad, kMapSw128)) return 1;
+                args.chunks[i] = (int)((ks[i] * e + 127) / 128);
+            }
+            if (!a2) args.chunks[1] = 0;
+            int stages = kPStagesMax;
+            while (stages > 2 && pcarve(tf32, Npad, (int)Hout, stages).total + 1024 > 227 * 1024) --stages;
+            if (pcarve(tf32, Npad, (int)Hout, stages).total + 1024 <= 227 * 1024) {
+                args.stages = stages;
+                const size_t psmem = pcarve(tf32, Npad, (int)Hout, stages).total + 1024;
+                const unsigned grid = (unsigned)std::min<int64_t>(tiles64, kNumSMs);
+                if (tf32) {
+                    auto kern = k_linear_tcp<float, true>;
+                    DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                    kern<<<grid, kPThreads, psmem, s>>>(pm, args, (int)tiles64);
+                } else {
+                    auto kern = k_linear_tcp<__nv_bfloat16, false>;
+                    DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                    kern<<<grid, kPThreads, psmem, s>>>(pm, args, (int)tiles64);
+                }
+                DFW_LAUNCH_CHECK();
+                return 0;
+            }
+        }
+    }
+
     Maps maps;
     memset(&maps, 0, sizeof(maps));
     args.Npad = (int)((Hout + 15) / 16 * 16);
@@ -715,8 +1134,6 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
         args.chunks[i] = (int)((ks[i] * e + cb - 1) / cb);
     }
     if (!a2) args.chunks[1] = 0;
-    if (args.out && make_map(&maps.out, args.out, args.N, Hout, e, kTileM)) return 1;
-    if (args.pre_out && make_map(&maps.pre, args.pre_out, args.N, Hout, e, kTileM)) return 1;
     if (args.residual && make_map(&maps.res, args.residual, args.N, Hout, e, kTileM)) return 1;
     const int out_boxes = (int)(Hout * e / kChunkBytes);
 
