@@ -334,6 +334,8 @@ def aggregation_cfg4(device, pk, iters=20):
         amin = 2 * n * H * 2 + 4 * E + 4 * (n + 1)
         ent = {"N": n, "E": E, "A_min_MB": round(amin / 1e6, 1), "A_gather_MB": round((E * H * 2 + n * H * 2 + 4 * E + 4 * (n + 1)) / 1e6, 1)}
         for name, (fn, info) in ops.cfg4_aggregation_paths(ei, n, pos_n, x).items():
+            if os.environ.get("DFW_BENCH_VERBOSE"):
+                print(f"[cfg4] {order} {name}", file=sys.stderr, flush=True)
             for _ in range(3):
                 fn()
             ts = []

@@ -58,6 +58,7 @@ constexpr int kSortCap = 4096;    // power of two >= kPlanCap (bitonic sort in t
 constexpr int kIdxRing = 8;
 constexpr int kThreads = 640;
 constexpr int kProducerWarps = 8;
+constexpr int kOwnChunks = kBlockRows / kChunk;  // a block's first 128 staged rows are its own rows (plan slots 0 .. 127)
 constexpr int kMaxStages = 3;      // measured on config 4 (k-d order): 2 / 3 / 4 stages = 638 / 537 / 549 us - not latency bound beyond 3
 constexpr int kStagingBoxes = 1;  // shared memory goes to the pipeline (bytes in flight bound this kernel), not to the epilogue
 
@@ -88,8 +89,8 @@ __host__ __device__ inline Layout carve(int H, int stages) {
     L.blkbuf_bytes = 288u + kPlanCap * 2u;            // record (272 B, padded) + slots
     L.idx = L.blkbuf + 2u * L.blkbuf_bytes;
     L.flags = L.idx + kIdxRing * kChunk * 4u;
-    L.bars = L.flags + kIdxRing * 4u;
-    L.total = L.bars + 8u * (2 * kMaxStages + 2 * kIdxRing + 8) + 16u;
+    L.bars = L.flags + kIdxRing * 8u;
+    L.total = L.bars + 8u * (3 * kMaxStages + 2 * kIdxRing + 8) + 16u;
     return L;
 }
 
@@ -110,7 +111,7 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ int chunks_of(int S) { return (max(S, 1) + kChunk - 1) / kChunk; }
+__device__ __forceinline__ int chunks_of(int S) { return (max(S, kBlockRows) + kChunk - 1) / kChunk; }
 // mbarrier wait whose try_wait carries a suspend-time hint: the warp sleeps in hardware until the phase completes (or the
 // hint expires) instead of spinning through issue slots - 16 of this kernel's 20 warps are waiting at any time, and the
 // plain spin loop took half of all issue cycles (ncu r02c: 24 M + 19 M loop iterations per launch).
@@ -135,15 +136,16 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 }
 #define mbar_wait mbar_wait_sleep
 
-__global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const __grid_constant__ CUtensorMap map_x, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const Layout L = carve(p.H, p.stages);
-    uint32_t* idx_flag = reinterpret_cast<uint32_t*>(smem + L.flags);  // 1 = the ring slot holds a chunk, 0 = end of stream
+    int2* idx_flag = reinterpret_cast<int2*>(smem + L.flags);  // .x: 0 = end of stream, 1 = gathered chunk (64 indices in the ring slot), 2 = the block's OWN rows .y .. .y+63
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);       // [stages]  producers (8) + adjacency warps (4)
     uint64_t* empty = full + kMaxStages;                               // [stages]  tcgen05.commit
-    uint64_t* idx_full = empty + kMaxStages;                           // [ring]    loader (tx bytes)
-    uint64_t* idx_empty = idx_full + kIdxRing;                         // [ring]    producer warps (8)
+    uint64_t* zfull = empty + kMaxStages;                              // [stages]  the ADJ tile of the stage has been zero-filled (TMA)
+    uint64_t* idx_full = zfull + kMaxStages;                           // [ring]    loader (tx bytes)
+    uint64_t* idx_empty = idx_full + kIdxRing;                         // [ring]    producer warps (8) + the tile producer
     uint64_t* blk_full = idx_empty + kIdxRing;                         // [2]       loader (tx bytes)
     uint64_t* blk_empty = blk_full + 2;                                // [2]       adjacency warps (4)
     uint64_t* acc_full = blk_empty + 2;                                // [2]       tcgen05.commit
@@ -157,12 +159,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full[s], kProducerWarps * 32 + 4);  // every producer lane (cp.async completion) + the adjacency warps
+            mbar_init(&full[s], kProducerWarps * 32 + 4 + 1);  // every producer lane (cp.async completion), the adjacency warps, the tile producer
             mbar_init(&empty[s], 1);
+            mbar_init(&zfull[s], 1);
         }
         for (int r = 0; r < kIdxRing; ++r) {
             mbar_init(&idx_full[r], 1);
-            mbar_init(&idx_empty[r], kProducerWarps);
+            mbar_init(&idx_empty[r], kProducerWarps + 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&blk_full[b], 1);
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
             mbar_init(&acc_empty[b], 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&map_x);
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(tmem_cols) : "memory");
@@ -201,17 +205,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
                 for (int c = 0; c < nch; ++c, ++g) {
                     const int r = g % kIdxRing;
                     mbar_wait(&idx_empty[r], (uint32_t)(((g / kIdxRing) & 1) ^ 1));
-                    idx_flag[r] = 1u;
-                    mbar_arrive_expect_tx(&idx_full[r], kChunk * 4u);
-                    bulk_g2s(smem + L.idx + (size_t)r * kChunk * 4, p.plan_src + (size_t)meta.x + (size_t)c * kChunk, kChunk * 4u, &idx_full[r]);
+                    if (c < kOwnChunks) {  // the block's own rows: consecutive, fetched as plain TMA tiles by the tile producer
+                        idx_flag[r] = make_int2(2, b * kBlockRows + c * kChunk);
+                        mbar_arrive(&idx_full[r]);
+                    } else {
+                        idx_flag[r] = make_int2(1, 0);
+                        mbar_arrive_expect_tx(&idx_full[r], kChunk * 4u);
+                        bulk_g2s(smem + L.idx + (size_t)r * kChunk * 4, p.plan_src + (size_t)meta.x + (size_t)c * kChunk, kChunk * 4u, &idx_full[r]);
+                    }
                 }
             }
             const int r = g % kIdxRing;  // end of stream
             mbar_wait(&idx_empty[r], (uint32_t)(((g / kIdxRing) & 1) ^ 1));
-            idx_flag[r] = 0u;
+            idx_flag[r] = make_int2(0, 0);
             mbar_arrive(&idx_full[r]);
         } else if (lane == 0) {
-            idx_flag[0] = 0u;
+            idx_flag[0] = make_int2(0, 0);
             mbar_arrive(&idx_full[0]);
         }
     } else if (warp == 1) {
@@ -246,6 +255,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&acc_full[ab]);
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== tile producer (one thread, TMA only) =====================
+        // Per chunk: (1) zero-fills the stage's ADJ tile with two fully out-of-bounds tile loads (the TMA unit writes zeros, no
+        // global read, no LSU traffic - the adjacency warps used to spend 8 STS.128 + a named barrier per chunk on this);
+        // (2) for the block's own rows (chunks 0, 1) loads the 64 consecutive rows as ordinary [64 rows x 128 B] tiles - a
+        // third of all staged rows never touches the LSU.
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int nbox = H >> 6;
+            const int oob_row = (int)min((int64_t)0x7ffffff0, p.N + 4096);
+            for (int g = 0;; ++g) {
+                const int r = g & (kIdxRing - 1);
+                mbar_wait(&idx_full[r], (uint32_t)((g / kIdxRing) & 1));
+                const int2 f = idx_flag[r];
+                if (f.x == 0) break;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + (size_t)stage * L.stage;
+                mbar_arrive_expect_tx(&zfull[stage], L.a_bytes);
+                tma_load_2d(st + L.b_bytes, &map_x, &zfull[stage], 0, oob_row);
+                tma_load_2d(st + L.b_bytes + kChunk * 128, &map_x, &zfull[stage], 0, oob_row);
+                if (f.x == 2) {
+                    mbar_arrive_expect_tx(&full[stage], L.b_bytes);
+                    for (int bx = 0; bx < nbox; ++bx) tma_load_2d(st + (size_t)bx * (kChunk * 128), &map_x, &full[stage], bx * 64, f.y);
+                } else {
+                    mbar_arrive(&full[stage]);
+                }
+                mbar_arrive(&idx_empty[r]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -308,9 +348,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
         }
     } else if (warp >= 8 && warp < 12) {
         // ===================== adjacency builder =====================
-        // Per chunk: every thread clears its own 128-byte line of the ADJ tile, the four warps meet at a named barrier, then
-        // the chunk's plan entries (one per distinct (source, row) pair, already ordered by chunk) are applied flat, one
-        // 2-byte store each - no per-row walk, no divergence.  (The first version let thread m walk row m's slots with
+        // Per chunk: once the tile producer's TMA zero fill of the ADJ tile has landed, the chunk's plan entries (one per distinct
+        // (source, row) pair, already ordered by chunk) are applied flat, one 2-byte store each - no per-row walk, no
+        // divergence, no clearing by the LSU.  (The first version let thread m walk row m's slots with
         // data-dependent loops: ~900 clk per chunk, the bottleneck of the whole kernel - ncu r02e.)
         const int m = threadIdx.x - 256;
         int stage = 0;
@@ -323,13 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
             const uint16_t* ent = reinterpret_cast<const uint16_t*>(buf + 288);
             const int nch = chunks_of((int)rec[0]);
             for (int c = 0; c < nch; ++c) {
-                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_wait(&zfull[stage], phase);  // the tile is free (its MMAs retired) AND zero-filled
                 uint8_t* tile = smem + (size_t)stage * L.stage + L.b_bytes;
-                uint8_t* line = tile + (size_t)m * 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)  // staggered so that the 8 lanes of a quarter-warp hit 8 different bank groups
-                    *reinterpret_cast<uint4*>(line + ((j ^ (m & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-                asm volatile("bar.sync 2, 128;" ::: "memory");
                 const int t_end = rec[3 + c];
                 for (int t = (int)rec[2 + c] + m; t < t_end; t += 128) {
                     const uint32_t e = ent[t];
@@ -360,7 +395,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_aggregate_tc(const Params p) {
         for (int g = 0;; ++g) {
             const int r = g & (kIdxRing - 1);
             mbar_wait(&idx_full[r], (uint32_t)((g / kIdxRing) & 1));
-            if (idx_flag[r] == 0u) break;
+            const int kind = idx_flag[r].x;
+            if (kind == 0) break;
+            if (kind == 2) {  // own rows: the tile producer fetches them; this lane only accounts for its arrival - in the
+                // barrier's NEW phase: the stage's previous use must have been consumed first
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_arrive(&full[stage]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&idx_empty[r]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                continue;
+            }
             mbar_wait(&empty[stage], phase ^ 1);
             const int32_t* idx = reinterpret_cast<const int32_t*>(smem + L.idx + (size_t)r * kChunk * 4);
             const uint32_t sb = smem_u32(smem + (size_t)stage * L.stage) + dcol;
@@ -396,7 +441,7 @@ __global__ void k_plan_sizes(const int32_t* __restrict__ rowptr, int64_t N, int 
     if (b >= nblocks) return;
     const int64_t r0 = (int64_t)b * kBlockRows, r1 = min(N, r0 + kBlockRows);
     const int ne = rowptr[r1] - rowptr[r0];
-    sz[b] = (max(ne, 1) + kChunk - 1) / kChunk * kChunk;
+    sz[b] = (kBlockRows + ne + kChunk - 1) / kChunk * kChunk;  // own rows (always 128 slots) + at most one halo source per edge
     sz[nblocks + b] = (ne + 7) & ~7;
 }
 // exclusive scan of the two size arrays into blk_meta.x / .z (one CTA walks the blocks with a running carry)
@@ -430,12 +475,14 @@ __global__ void __launch_bounds__(1024) k_plan_scan(const int32_t* __restrict__ 
         __syncthreads();
     }
 }
-// one CTA per block: sort the block's edges by (source, row), number the distinct sources, emit the source list, the
+// one CTA per block: sort the block's edges by (own/halo, source, row), number the sources, emit the source list, the
 // chunk-sorted adjacency entries and the record
-//   plan_src  : ascending distinct sources, padded to a multiple of 64 with the last one (finite rows under zero ADJ columns)
+//   slots     : the block's OWN rows always hold slots 0 .. 127 (slot = row - first row, used or not: the kernel fetches them as
+//               two plain TMA tiles), the distinct HALO sources follow in ascending order from slot 128
+//   plan_src  : source row of every slot, padded to a multiple of 64 with the last one (finite rows under zero ADJ columns)
 //   plan_slot : one uint16 ENTRY per distinct (source, row) pair, ordered by (slot, row):  (count-1) << 13 | row << 6 | slot % 64
 //               - exactly the stores the kernel's adjacency warps perform, chunk c = entries [cptr[c], cptr[c+1])
-//   plan_rec  : [0] = S, [1] = number of entries, [2 .. 2 + nchunks] = cptr
+//   plan_rec  : [0] = S = 128 + #halo sources, [1] = number of entries, [2 .. 2 + nchunks] = cptr
 __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int4* __restrict__ meta,
                                                      int32_t* __restrict__ plan_src, uint16_t* __restrict__ plan_rec, uint16_t* __restrict__ plan_slot,
                                                      unsigned long long* __restrict__ status /*[0] max edges of a block, [1] sum of S*/) {
@@ -443,6 +490,7 @@ __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ 
     __shared__ uint16_t rowoff[kBlockRows + 1];
     __shared__ int wsum[2][8];
     __shared__ int s_total[2];
+    __shared__ int cmin[kRecU16];
     const int b = blockIdx.x;
     const int64_t r0 = (int64_t)b * kBlockRows;
     const int nr = (int)min((int64_t)kBlockRows, N - r0);
@@ -462,11 +510,22 @@ __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ 
     }
     if (threadIdx.x == 0) atomicMax(status, (unsigned long long)ne);
     for (int t = threadIdx.x; t <= kBlockRows; t += 256) rowoff[t] = (uint16_t)(rowptr[r0 + min(t, nr)] - e0);
-    for (int t = threadIdx.x; t < kRecU16; t += 256) rec[t] = 0;
+    for (int t = threadIdx.x; t < kRecU16; t += 256) {
+        rec[t] = 0;
+        cmin[t] = 0x7fffffff;
+    }
     int P = 2;
     while (P < ne) P <<= 1;
-    for (int t = threadIdx.x; t < P; t += 256)
-        key[t] = t < ne ? (((unsigned long long)(uint32_t)col[e0 + t] << 16) | (unsigned long long)t) : ~0ull;
+    const unsigned long long kHalo = 1ull << 62;
+    for (int t = threadIdx.x; t < P; t += 256) {
+        unsigned long long k = ~0ull;
+        if (t < ne) {
+            const int c = col[e0 + t];
+            const bool own = c >= r0 && c < r0 + nr;
+            k = (own ? 0ull : kHalo) | ((unsigned long long)(uint32_t)c << 16) | (unsigned long long)t;
+        }
+        key[t] = k;
+    }
     __syncthreads();
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -490,14 +549,16 @@ __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ 
         }
         return lo;
     };
+    auto src_of = [&](int t) { return (int)((key[t] >> 16) & 0xffffffffull); };
+    auto is_halo = [&](int t) { return (key[t] & kHalo) != 0; };
     auto src_head = [&](int t) { return t == 0 || (key[t] >> 16) != (key[t - 1] >> 16); };
     auto ent_head = [&](int t) { return src_head(t) || row_of((int)(key[t] & 0xffffu)) != row_of((int)(key[t - 1] & 0xffffu)); };
-    // two exclusive scans in one pass: distinct sources (slot numbers) and distinct (source, row) pairs (entry positions)
+    // two exclusive scans in one pass: distinct HALO sources (slot numbers from 128) and distinct (source, row) pairs (entry positions)
     const int per = (P + 255) / 256;
     const int t0 = threadIdx.x * per, t1 = min(t0 + per, ne);
     int local[2] = {0, 0};
     for (int t = t0; t < t1; ++t) {
-        local[0] += src_head(t) ? 1 : 0;
+        local[0] += (is_halo(t) && src_head(t)) ? 1 : 0;
         local[1] += ent_head(t) ? 1 : 0;
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -512,31 +573,41 @@ __global__ void __launch_bounds__(256) k_plan_block(const int32_t* __restrict__ 
     int off[2] = {inc[0] - local[0], inc[1] - local[1]};
     for (int w = 0; w < wid; ++w) { off[0] += wsum[0][w]; off[1] += wsum[1][w]; }
     if (threadIdx.x == 255) { s_total[0] = off[0] + local[0]; s_total[1] = off[1] + local[1]; }
-    int slot = off[0] - 1, epos = off[1] - 1;
+    int hslot = off[0] - 1, epos = off[1] - 1;
     for (int t = t0; t < t1; ++t) {
-        if (src_head(t)) {
-            ++slot;
-            plan_src[(size_t)mm.x + slot] = (int32_t)(key[t] >> 16);
+        const bool halo = is_halo(t);
+        if (halo && src_head(t)) {
+            ++hslot;
+            plan_src[(size_t)mm.x + kBlockRows + hslot] = src_of(t);
         }
         if (ent_head(t)) {
             ++epos;
+            const int slot = halo ? kBlockRows + hslot : src_of(t) - (int)r0;
             const int row = row_of((int)(key[t] & 0xffffu));
             int cnt = 1;  // multiplicity of a duplicate edge: the run of equal (source, row) may continue into the next thread's piece
             for (int u = t + 1; u < ne && !ent_head(u); ++u) ++cnt;
             if (cnt > 8) atomicMax(status, 1ull << 40);  // more than the 3-bit field holds: the plan is unusable
             plan_slot[(size_t)mm.z + epos] = (uint16_t)((min(cnt, 8) - 1) << 13 | row << 6 | (slot & (kChunk - 1)));
-            if (src_head(t) && (slot & (kChunk - 1)) == 0) rec[2 + slot / kChunk] = (uint16_t)epos;  // first entry of chunk slot / 64
+            atomicMin(&cmin[slot / kChunk], epos);  // first entry of chunk slot / 64
         }
     }
+    // own rows: slot i <-> row r0 + i (clamped inside the tensor for the ragged last block: those ADJ columns are empty)
+    for (int t = threadIdx.x; t < kBlockRows; t += 256) plan_src[(size_t)mm.x + t] = (int32_t)min(r0 + t, N - 1);
     __syncthreads();
-    const int S = s_total[0], nent = s_total[1];
-    const int padded = (max(S, 1) + kChunk - 1) / kChunk * kChunk;
-    const int32_t fill = S > 0 ? (int32_t)(key[ne - 1] >> 16) : 0;
+    const int S = kBlockRows + s_total[0], nent = s_total[1];
+    const int padded = (S + kChunk - 1) / kChunk * kChunk;
+    const int32_t fill = s_total[0] > 0 ? src_of(ne - 1) : (int32_t)min(r0 + kBlockRows - 1, N - 1);
     for (int t = S + threadIdx.x; t < padded; t += 256) plan_src[(size_t)mm.x + t] = fill;
     if (threadIdx.x == 0) {
+        const int nch = padded / kChunk;
+        int nxt = nent;  // chunks without entries (own rows nobody in the block points at) start where the next chunk starts
+        rec[2 + nch] = (uint16_t)nent;
+        for (int c = nch - 1; c >= 0; --c) {
+            if (cmin[c] != 0x7fffffff) nxt = cmin[c];
+            rec[2 + c] = (uint16_t)nxt;
+        }
         rec[0] = (uint16_t)S;
         rec[1] = (uint16_t)nent;
-        rec[2 + padded / kChunk] = (uint16_t)nent;  // cptr[nchunks] (an empty block has one all-zero chunk: cptr = {0, 0})
         mm.y = S;
         mm.w = nent;
         meta[b] = mm;
@@ -553,7 +624,7 @@ extern "C" int dfw_agg_plan_sizes(int64_t N, int64_t E, int64_t* nblocks, int64_
     DFW_REQUIRE(N >= 0 && E >= 0 && nblocks && src_cap && slot_cap, "dfw_agg_plan_sizes: bad arguments");
     const int64_t nb = (N + tcagg::kBlockRows - 1) / tcagg::kBlockRows;
     *nblocks = nb;
-    *src_cap = E + tcagg::kChunk * nb + tcagg::kChunk;
+    *src_cap = E + (tcagg::kBlockRows + tcagg::kChunk) * nb + tcagg::kChunk;
     *slot_cap = E + 8 * nb + 8;
     return 0;
 }
@@ -611,10 +682,13 @@ extern "C" int dfw_sage_aggregate_tc(const int32_t* blk_meta, const int32_t* pla
     p.stages = stages;
     const size_t smem = carve((int)H, stages).total + 1024;
     p.out = static_cast<uint8_t*>(out);
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (tc::make_map(&map, x, N, H, 2, kChunk)) return 1;  // [64 rows x 64 features] tiles of x: the blocks' own rows + the zero fill
     auto kern = k_aggregate_tc;
     DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)std::min<int64_t>(nb, kNumSMs);
-    kern<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    kern<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(map, p);
     DFW_LAUNCH_CHECK();
     return 0;
 }

@@ -124,7 +124,8 @@ int dfw_sage_aggregate_scaled(const int32_t* rowptr, const int32_t* col, const f
  * (b') the same mean / sum aggregation for bf16 rows on the tensor cores (block-sparse product; refined meshes, BASELINE.json
  *     config 4).  Replaces the same PyG expression as dfw_sage_aggregate (index_select + scatter_add_ + divide behind
  *     SAGEConv(aggr='mean'), call site model.py:90).  Rows are cut into blocks of 128 consecutive rows; a one-time PLAN of the
- *     CSR lists per block its distinct source rows (plan_src, padded to multiples of 64) and one 16-bit entry per distinct
+ *     CSR lists per block its source rows (plan_src: the block's own 128 rows first - the kernel fetches those as plain TMA
+ *     tiles - then the distinct other sources ascending, padded to multiples of 64) and one 16-bit entry per distinct
  *     (source, row) pair - (multiplicity-1) << 13 | row << 6 | slot % 64, ordered by 64-source chunk (plan_slot) - with the
  *     chunk pointers in the block record (plan_rec: S, #entries, cptr[...]); per block  OUT[128,H] = ADJ[128,S] . X[S,H]
  *     runs as tcgen05.mma with fp32 accumulation (ADJ = edge multiplicities: exact products), row_scale in the epilogue.
