@@ -545,6 +545,217 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
     if (threadIdx.x == 0) PROBE(48);
 }
 
+// The three epilogue passes of one 128-row tile for ONE thread (= tile row `q*32 + lane`, whose accumulator lives in TMEM lane
+// `q*32 + lane` from column `t_row`): y = (acc + bias) * row_scale, LayerNorm, ReLU, dropout, row-dot, residual, stores through the
+// warp's private staging slice.  Shared by the persistent kernels (k_linear_tcp, k_linear_tc2).
+template <typename T, bool TF32>
+__device__ __forceinline__ void epilogue_tile(const Args& p, const float* cvec, int HP, uint8_t* slice, uint32_t t_row, int64_t m_base, int q, int lane) {
+    constexpr int SCOLS = 64 / (int)sizeof(T);  // columns per 64-byte staging round: 16 fp32 / 32 bf16
+    const int r_in_tile = q * 32 + lane;
+    const int H = p.Hout;
+    const int n32 = H / 32;
+    const bool ln = p.flags & DFW_EP_LAYERNORM, relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
+    const float4* bias4 = reinterpret_cast<const float4*>(cvec);
+    const float4* gam4 = reinterpret_cast<const float4*>(cvec + HP);
+    const float4* bet4 = reinterpret_cast<const float4*>(cvec + 2 * HP);
+    const float4* rdw4 = reinterpret_cast<const float4*>(cvec + 3 * HP);
+    const uint32_t row_bytes = (uint32_t)H * (uint32_t)sizeof(T);
+    const bool y_in_tmem = ln || p.pre_out;
+    const int64_t row = m_base + r_in_tile;
+    const bool rok = row < p.N;
+    const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
+    const uint32_t row_key = drop ? dropout_row_key(resolve_seed(p.seed, p.flags), (uint64_t)row) : 0u;
+
+    // one 64-byte piece per row of this warp's 32 rows -> global, coalesced (4 lanes = one row piece), + residual.
+    // The residual pieces of the NEXT 64-byte round are requested before this round is staged, so their latency runs under the
+    // staging, the stores and the next group's TMEM load + math (loaded on demand they cost ~1 us per round: 8 us per fp32 tile).
+    uint4 rpre[4];
+    int rpre_col = -1;
+    auto load_res = [&](const void* rbase, int col0, uint4 (&dst)[4]) {
+        const size_t coff = (size_t)col0 * sizeof(T) + (size_t)(lane & 3) * 16;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int64_t grow = m_base + q * 32 + it * 8 + (lane >> 2);
+            dst[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (grow < p.N) dst[it] = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(rbase) + (size_t)grow * row_bytes + coff);
+        }
+    };
+    auto write_out = [&](void* gbase, const void* rbase, int col0, const uint4 (&pk)[4]) {
+        uint4 rv[4];
+        if (rbase) {
+            if (rpre_col == col0) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) rv[it] = rpre[it];
+            } else {
+                load_res(rbase, col0, rv);
+            }
+            if (col0 + SCOLS < H) {
+                load_res(rbase, col0 + SCOLS, rpre);
+                rpre_col = col0 + SCOLS;
+            }
+        }
+        __syncwarp();  // the previous round's read-back is done
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slice + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk[j];
+        __syncwarp();
+        const int jj = lane & 3;
+        const size_t coff = (size_t)col0 * sizeof(T) + (size_t)jj * 16;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2);
+            uint4 v = *reinterpret_cast<const uint4*>(slice + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
+            const int64_t grow = m_base + q * 32 + rr;
+            if (grow < p.N) {
+                const size_t off = (size_t)grow * row_bytes + coff;
+                if (rbase) {
+                    const uint4 r4 = rv[it];
+                    if constexpr (sizeof(T) == 4) {
+                        v.x = __float_as_uint(__uint_as_float(v.x) + __uint_as_float(r4.x));
+                        v.y = __float_as_uint(__uint_as_float(v.y) + __uint_as_float(r4.y));
+                        v.z = __float_as_uint(__uint_as_float(v.z) + __uint_as_float(r4.z));
+                        v.w = __float_as_uint(__uint_as_float(v.w) + __uint_as_float(r4.w));
+                    } else {
+                        Vec16<T> a, b;
+                        a.v = v;
+                        b.v = r4;
+                        float fa[8], fb[8];
+                        a.to_float(fa);
+                        b.to_float(fb);
+#pragma unroll
+                        for (int e8 = 0; e8 < 8; ++e8) fa[e8] += fb[e8];
+                        a.from_float(fa);
+                        v = a.v;
+                    }
+                }
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(gbase) + off) = v;
+            }
+        }
+    };
+    // 32 fp32 values of this thread's row (columns c0 .. c0+31) -> T -> global
+    auto emit32 = [&](void* gbase, const void* rbase, int c0, const float* v) {
+        if constexpr (sizeof(T) == 4) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint4 pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    pk[j] = make_uint4(__float_as_uint(v[h * 16 + 4 * j]), __float_as_uint(v[h * 16 + 4 * j + 1]), __float_as_uint(v[h * 16 + 4 * j + 2]),
+                                       __float_as_uint(v[h * 16 + 4 * j + 3]));
+                write_out(gbase, rbase, c0 + h * SCOLS, pk);
+            }
+        } else {
+            uint4 pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                Vec16<T> u;
+                u.from_float(v + 8 * j);
+                pk[j] = u.v;
+            }
+            write_out(gbase, rbase, c0, pk);
+        }
+    };
+    // y = (acc + bias) * row_scale for the 32 columns starting at c0
+    auto finish_y = [&](int c0, float* v) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float4 b = bias4[c0 / 4 + g];
+            v[4 * g] = (v[4 * g] + b.x) * rs;
+            v[4 * g + 1] = (v[4 * g + 1] + b.y) * rs;
+            v[4 * g + 2] = (v[4 * g + 2] + b.z) * rs;
+            v[4 * g + 3] = (v[4 * g + 3] + b.w) * rs;
+        }
+    };
+    auto load_acc = [&](int c0, float* v) {  // hi*hi + cross terms, summed in round-to-nearest fp32 (see tmem_combine)
+        tmem_ld32(t_row + c0, v);
+        if (TF32) {
+            float w[32];
+            tmem_ld32(t_row + p.Npad + c0, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
+    };
+    float mean = 0.f, rstd = 1.f;
+    // ---- pass 1: y written back to region 0, row sum, pre-activation tensor ----
+    if (y_in_tmem) {
+        float s = 0.f;
+        for (int g = 0; g < n32; ++g) {
+            const int c0 = g * 32;
+            float v[32];
+            load_acc(c0, v);
+            finish_y(c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += v[j];
+            tmem_st32_nowait(t_row + c0, v);
+            if (p.pre_out) emit32(p.pre_out, nullptr, c0, v);
+        }
+        tmem_st_wait();
+        mean = s / (float)H;
+    }
+    // ---- pass 2: variance around the mean (two-pass, like torch) ----
+    if (ln) {
+        float qs = 0.f;
+        for (int g = 0; g < n32; ++g) {
+            float v[32];
+            tmem_ld32(t_row + g * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float d = v[j] - mean;
+                qs = fmaf(d, d, qs);
+            }
+        }
+        rstd = rsqrtf(qs / (float)H + p.eps);
+        if (p.ln_stats && rok) {
+            p.ln_stats[2 * row] = mean;
+            p.ln_stats[2 * row + 1] = rstd;
+        }
+    }
+    // ---- pass 3: normalise, ReLU, dropout, row-dot, (+ residual in the write-back), store ----
+    float dot = 0.f;
+    for (int g = 0; g < n32; ++g) {
+        const int c0 = g * 32;
+        float v[32];
+        if (y_in_tmem) {
+            tmem_ld32(t_row + c0, v);
+        } else {
+            load_acc(c0, v);
+            finish_y(c0, v);
+        }
+        if (ln) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const float4 ga = gam4[c0 / 4 + g4], be = bet4[c0 / 4 + g4];
+                v[4 * g4] = (v[4 * g4] - mean) * rstd * ga.x + be.x;
+                v[4 * g4 + 1] = (v[4 * g4 + 1] - mean) * rstd * ga.y + be.y;
+                v[4 * g4 + 2] = (v[4 * g4 + 2] - mean) * rstd * ga.z + be.z;
+                v[4 * g4 + 3] = (v[4 * g4 + 3] - mean) * rstd * ga.w + be.w;
+            }
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (drop) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t bits = dropout_bits(row_key, (uint32_t)(c0 + j));
+                v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
+            }
+        }
+        if (p.rowdot_out) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const float4 w = rdw4[c0 / 4 + g4];
+                dot = fmaf(v[4 * g4], w.x, dot);
+                dot = fmaf(v[4 * g4 + 1], w.y, dot);
+                dot = fmaf(v[4 * g4 + 2], w.z, dot);
+                dot = fmaf(v[4 * g4 + 3], w.w, dot);
+            }
+        }
+        if (p.out) emit32(p.out, p.residual, c0, v);
+    }
+    if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
+}
+
 // =====================================================================================================================
 // Persistent variant: one CTA per SM loops over 128-row tiles.
 //   * K chunks of 128 bytes (SWIZZLE_128B) for fp32 too: the TMA unit retires ~one box ROW per 2 clk whatever its width
@@ -582,7 +793,6 @@ __host__ __device__ inline PLayout pcarve(bool tf32, int Npad, int Hout, int sta
 template <typename T, bool TF32>
 __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_constant__ Maps maps, const Args p, const int num_tiles) {
     constexpr int KPC = 128 / (int)sizeof(T);   // K elements per 128-byte chunk
-    constexpr int SCOLS = 64 / (int)sizeof(T);  // columns per 64-byte staging round: 16 fp32 / 32 bf16
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const PLayout L = pcarve(TF32, p.Npad, p.Hout, p.stages);
@@ -634,7 +844,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
     fence_tc_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
+    // Register budget per warpgroup (512 threads x 128 at launch): the producer / MMA / converter warpgroups give registers back,
+    // the two epilogue warpgroups take 168 each (setmaxnreg sits at the head of each role's branch so that ptxas allocates the
+    // branch against the new limit).
+    if (warp < 4) {
+      if constexpr (TF32) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             const uint32_t stage_tx = (uint32_t)(kTileM * 128 + p.Npad * 128 * (TF32 ? 2 : 1));
@@ -655,7 +870,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t fmt = TF32 ? 2u : 1u;
@@ -693,8 +908,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
                 umma_commit(&acc_full[ab]);
             }
         }
+      }
     } else if (warp >= 12) {
         // ===== converters (fp32): a_lo = a - trunc_tf32(a), in place beside the TMA tile =====
+        if constexpr (TF32) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (TF32) {
             const int ct = threadIdx.x - 384;
             int stage = 0;
@@ -713,196 +930,21 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else {
         // ===== epilogue warpgroups: WG0 (warps 4-7) takes even tiles, WG1 (warps 8-11) odd tiles =====
+        if constexpr (TF32) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");  // (bf16 measured 8 % slower with the re-balancing: left alone)
         const int wg = (warp - 4) >> 2;
         const int q = warp & 3;  // TMEM lane quarter
-        const int r_in_tile = q * 32 + lane;
-        const int H = p.Hout;
-        const int n32 = H / 32;
-        const bool ln = p.flags & DFW_EP_LAYERNORM, relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
-        const uint64_t seed = drop ? resolve_seed(p.seed, p.flags) : 0ull;
-        const float4* bias4 = reinterpret_cast<const float4*>(cvec);
-        const float4* gam4 = reinterpret_cast<const float4*>(cvec + HP);
-        const float4* bet4 = reinterpret_cast<const float4*>(cvec + 2 * HP);
-        const float4* rdw4 = reinterpret_cast<const float4*>(cvec + 3 * HP);
         uint8_t* slice = smem + L.staging + (size_t)(warp - 4) * 2048;  // this warp's [32 rows x 64 B]
-        const uint32_t row_bytes = (uint32_t)H * (uint32_t)sizeof(T);
-        const bool y_in_tmem = ln || p.pre_out;
 
         for (int i = wg; i < nmine; i += 2) {
             const int64_t m_base = (int64_t)((int)blockIdx.x + i * (int)gridDim.x) * kTileM;
-            const int64_t row = m_base + r_in_tile;
-            const bool rok = row < p.N;
             const int ab = i & 1;
-            const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
-            const uint32_t row_key = drop ? dropout_row_key(seed, (uint64_t)row) : 0u;
             mbar_wait(&acc_full[ab], (uint32_t)((i >> 1) & 1));
             fence_tc_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * buf_cols;
 
-            // one 64-byte piece per row of this warp's 32 rows -> global, coalesced (4 lanes = one row piece), + residual
-            auto write_out = [&](void* gbase, const void* rbase, int col0, const uint4 (&pk)[4]) {
-                __syncwarp();  // the previous round's read-back is done
-#pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slice + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk[j];
-                __syncwarp();
-                const int jj = lane & 3;
-                const size_t coff = (size_t)col0 * sizeof(T) + (size_t)jj * 16;
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int rr = it * 8 + (lane >> 2);
-                    uint4 v = *reinterpret_cast<const uint4*>(slice + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
-                    const int64_t grow = m_base + q * 32 + rr;
-                    if (grow < p.N) {
-                        const size_t off = (size_t)grow * row_bytes + coff;
-                        if (rbase) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(rbase) + off);
-                            if constexpr (sizeof(T) == 4) {
-                                v.x = __float_as_uint(__uint_as_float(v.x) + __uint_as_float(rv.x));
-                                v.y = __float_as_uint(__uint_as_float(v.y) + __uint_as_float(rv.y));
-                                v.z = __float_as_uint(__uint_as_float(v.z) + __uint_as_float(rv.z));
-                                v.w = __float_as_uint(__uint_as_float(v.w) + __uint_as_float(rv.w));
-                            } else {
-                                Vec16<T> a, b;
-                                a.v = v;
-                                b.v = rv;
-                                float fa[8], fb[8];
-                                a.to_float(fa);
-                                b.to_float(fb);
-#pragma unroll
-                                for (int e8 = 0; e8 < 8; ++e8) fa[e8] += fb[e8];
-                                a.from_float(fa);
-                                v = a.v;
-                            }
-                        }
-                        *reinterpret_cast<uint4*>(static_cast<uint8_t*>(gbase) + off) = v;
-                    }
-                }
-            };
-            // 32 fp32 values of this thread's row (columns c0 .. c0+31) -> T -> global
-            auto emit32 = [&](void* gbase, const void* rbase, int c0, const float* v) {
-                if constexpr (sizeof(T) == 4) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint4 pk[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            pk[j] = make_uint4(__float_as_uint(v[h * 16 + 4 * j]), __float_as_uint(v[h * 16 + 4 * j + 1]), __float_as_uint(v[h * 16 + 4 * j + 2]),
-                                               __float_as_uint(v[h * 16 + 4 * j + 3]));
-                        write_out(gbase, rbase, c0 + h * SCOLS, pk);
-                    }
-                } else {
-                    uint4 pk[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        Vec16<T> u;
-                        u.from_float(v + 8 * j);
-                        pk[j] = u.v;
-                    }
-                    write_out(gbase, rbase, c0, pk);
-                }
-            };
-            // y = (acc + bias) * row_scale for the 32 columns starting at c0
-            auto finish_y = [&](int c0, float* v) {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float4 b = bias4[c0 / 4 + g];
-                    v[4 * g] = (v[4 * g] + b.x) * rs;
-                    v[4 * g + 1] = (v[4 * g + 1] + b.y) * rs;
-                    v[4 * g + 2] = (v[4 * g + 2] + b.z) * rs;
-                    v[4 * g + 3] = (v[4 * g + 3] + b.w) * rs;
-                }
-            };
-            auto load_acc = [&](int c0, float* v) {  // hi*hi + cross terms, summed in round-to-nearest fp32 (see tmem_combine)
-                tmem_ld32(t_row + c0, v);
-                if (TF32) {
-                    float w[32];
-                    tmem_ld32(t_row + p.Npad + c0, w);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += w[j];
-                }
-            };
-            float mean = 0.f, rstd = 1.f;
-            // ---- pass 1: y written back to region 0, row sum, pre-activation tensor ----
-            if (y_in_tmem) {
-                float s = 0.f;
-                for (int g = 0; g < n32; ++g) {
-                    const int c0 = g * 32;
-                    float v[32];
-                    load_acc(c0, v);
-                    finish_y(c0, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) s += v[j];
-                    tmem_st32_nowait(t_row + c0, v);
-                    if (p.pre_out) emit32(p.pre_out, nullptr, c0, v);
-                }
-                tmem_st_wait();
-                mean = s / (float)H;
-            }
-            // ---- pass 2: variance around the mean (two-pass, like torch) ----
-            if (ln) {
-                float qs = 0.f;
-                for (int g = 0; g < n32; ++g) {
-                    float v[32];
-                    tmem_ld32(t_row + g * 32, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float d = v[j] - mean;
-                        qs = fmaf(d, d, qs);
-                    }
-                }
-                rstd = rsqrtf(qs / (float)H + p.eps);
-                if (p.ln_stats && rok) {
-                    p.ln_stats[2 * row] = mean;
-                    p.ln_stats[2 * row + 1] = rstd;
-                }
-            }
-            // ---- pass 3: normalise, ReLU, dropout, row-dot, (+ residual in the write-back), store ----
-            float dot = 0.f;
-            for (int g = 0; g < n32; ++g) {
-                const int c0 = g * 32;
-                float v[32];
-                if (y_in_tmem) {
-                    tmem_ld32(t_row + c0, v);
-                } else {
-                    load_acc(c0, v);
-                    finish_y(c0, v);
-                }
-                if (ln) {
-#pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 ga = gam4[c0 / 4 + g4], be = bet4[c0 / 4 + g4];
-                        v[4 * g4] = (v[4 * g4] - mean) * rstd * ga.x + be.x;
-                        v[4 * g4 + 1] = (v[4 * g4 + 1] - mean) * rstd * ga.y + be.y;
-                        v[4 * g4 + 2] = (v[4 * g4 + 2] - mean) * rstd * ga.z + be.z;
-                        v[4 * g4 + 3] = (v[4 * g4 + 3] - mean) * rstd * ga.w + be.w;
-                    }
-                }
-                if (relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (drop) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const uint32_t bits = dropout_bits(row_key, (uint32_t)(c0 + j));
-                        v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
-                    }
-                }
-                if (p.rowdot_out) {
-#pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 w = rdw4[c0 / 4 + g4];
-                        dot = fmaf(v[4 * g4], w.x, dot);
-                        dot = fmaf(v[4 * g4 + 1], w.y, dot);
-                        dot = fmaf(v[4 * g4 + 2], w.z, dot);
-                        dot = fmaf(v[4 * g4 + 3], w.w, dot);
-                    }
-                }
-                if (p.out) emit32(p.out, p.residual, c0, v);
-            }
-            if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
+            epilogue_tile<T, TF32>(p, cvec, HP, slice, t_row, m_base, q, lane);
             fence_tc_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[ab]);
@@ -914,6 +956,272 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
     if (warp == 2) {
         fence_tc_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster (one TPC) issue ONE tcgen05.mma over their two 128-row tiles
+// (M = 256); the B operand (weights) is split by output columns between the two CTAs, so each CTA holds HALF of the weight
+// bytes - small enough to stay RESIDENT in shared memory for the whole kernel (fp32 H = 128, K = 256: 128 KB per CTA for hi + lo).
+// Per tile only the activations stream through the TMA ring (k_linear_tc re-fetches 2/3 of every stage - the weights - from L2
+// for every 128 rows; tools/probes/tma_rate_probe.cu and the ncu captures show that stream, not HBM, pacing its main loop).
+//   leader CTA (rank 0): its MMA thread issues for both; tcgen05.commit multicasts to both CTAs' barriers
+//   both CTAs: own TMA producer (own activation tile), own converters (fp32 a_lo) which signal the LEADER's `ready` barrier
+//   (remote mbarrier arrive), own two epilogue warpgroups draining their own TMEM (double-buffered accumulators), which release
+//   the accumulator buffer on the leader's `acc_empty` barrier.
+// fp32: three MMAs per k-step (a_hi.w_hi -> main; a_lo.w_hi, a_hi.w_lo -> cross), each M = 256, N = Npad.
+// =====================================================================================================================
+constexpr int k2Threads = 512;
+constexpr int k2StagesMax = 6;
+
+struct Layout2 {
+    uint32_t cb, w_chunk, w_lo_off, w_bytes, a_hi, a_lo, stage_bytes, stages_off, staging, cvec, bars, total;
+};
+__host__ __device__ inline Layout2 carve2(bool tf32, int Npad, int Hout, int total_chunks, int stages) {
+    Layout2 L;
+    L.cb = tf32 ? 64u : 128u;                                   // K bytes per chunk (fp32: SWIZZLE_64B, bf16: SWIZZLE_128B)
+    const uint32_t wh = (uint32_t)(Npad / 2) * L.cb;            // this CTA's half of the weight rows, one chunk
+    L.w_lo_off = (wh + 1023u) / 1024u * 1024u;
+    L.w_chunk = tf32 ? 2 * L.w_lo_off : L.w_lo_off;
+    L.w_bytes = L.w_chunk * (uint32_t)total_chunks;
+    const uint32_t a = kTileM * L.cb;
+    L.a_hi = 0;
+    L.a_lo = a;
+    L.stage_bytes = tf32 ? 2 * a : a;
+    L.stages_off = L.w_bytes;
+    L.staging = L.stages_off + L.stage_bytes * (uint32_t)stages;
+    L.cvec = L.staging + 8u * 2048u;
+    L.bars = L.cvec + 4u * (uint32_t)((Hout + 31) / 32 * 32) * 4u;
+    L.total = L.bars + 8u * (3 * k2StagesMax + 5) + 16u;
+    return L;
+}
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // barrier also signalled by the peer CTA
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 24)) {
+            printf("dfw_linear_tc2: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+            __trap();
+        }
+    } while (!ok);
+}
+template <bool TF32>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(adesc),
+                     "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    } else {
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(adesc),
+                     "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {  // arrive on this barrier offset in BOTH CTAs once the MMAs issued so far retire
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <typename T, bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) k_linear_tc2(const __grid_constant__ Maps maps, const Args p, const int num_pairs) {
+    constexpr int CB = TF32 ? 64 : 128;
+    constexpr int KPC = CB / (int)sizeof(T);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int total_chunks = p.chunks[0] + p.chunks[1];
+    const Layout2 L = carve2(TF32, p.Npad, p.Hout, total_chunks, p.stages);
+    const int HP = (p.Hout + 31) / 32 * 32;
+    float* cvec = reinterpret_cast<float*>(smem + L.cvec);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);  // [stages] local: this CTA's activation chunk landed
+    uint64_t* empty = full + k2StagesMax;                          // [stages] both: MMAs that read the stage retired (multicast commit)
+    uint64_t* ready = empty + k2StagesMax;                         // [stages] LEADER's: both CTAs' operands of the stage are ready
+    uint64_t* acc_full = ready + k2StagesMax;                      // [2] both (multicast commit)
+    uint64_t* acc_empty = acc_full + 2;                            // [2] LEADER's: both CTAs' epilogues drained the buffer
+    uint64_t* w_full = acc_empty + 2;                              // local: this CTA's resident weights landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair0 = (int)blockIdx.x >> 1, npc = (int)gridDim.x >> 1;  // this cluster's first tile pair, number of clusters
+    const int nmine = pair0 < num_pairs ? (num_pairs - 1 - pair0) / npc + 1 : 0;
+    const int regions = TF32 ? 2 : 1;
+    const uint32_t buf_cols = (uint32_t)(regions * p.Npad);
+    const int ready_count = TF32 ? 8 : 2;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&ready[s], ready_count);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 8);
+        }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&maps.a[0]);
+        prefetch_tmap(&maps.w_hi[0]);
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int c = threadIdx.x; c < p.Hout; c += k2Threads) {
+        cvec[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+        cvec[HP + c] = p.gamma ? __ldg(p.gamma + c) : 1.f;
+        cvec[2 * HP + c] = p.beta ? __ldg(p.beta + c) : 0.f;
+        cvec[3 * HP + c] = p.rowdot_w ? __ldg(p.rowdot_w + c) : 0.f;
+    }
+    fence_tc_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers exist before anything is signalled across the pair
+    fence_tc_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t ready_leader = map_to_cta(smem_u32(ready), 0);        // + 8 * stage
+    const uint32_t acc_empty_leader = map_to_cta(smem_u32(acc_empty), 0);  // + 8 * buffer
+
+    if (warp == 0) {
+        // ===== TMA producer: the resident weight half once, then this CTA's activation tiles =====
+        if (lane == 0) {
+            const int half = p.Npad / 2;
+            mbar_arrive_expect_tx(w_full, (uint32_t)(total_chunks * half * CB * (TF32 ? 2 : 1)));
+            for (int c = 0; c < total_chunks; ++c) {
+                const int seg = c >= p.chunks[0];
+                const int kc = (seg ? c - p.chunks[0] : c) * KPC;
+                uint8_t* wc = smem + (size_t)c * L.w_chunk;
+                tma_load_2d(wc, &maps.w_hi[seg], w_full, kc, (int)rank * half);
+                if (TF32) tma_load_2d(wc + L.w_lo_off, &maps.w_lo[seg], w_full, kc, (int)rank * half);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nmine; ++i) {
+                const int m_base = (2 * (pair0 + i * npc) + (int)rank) * kTileM;
+                for (int c = 0; c < total_chunks; ++c) {
+                    const int seg = c >= p.chunks[0];
+                    const int kc = (seg ? c - p.chunks[0] : c) * KPC;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = smem + L.stages_off + (size_t)stage * L.stage_bytes;
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(kTileM * CB));
+                    tma_load_2d(st + L.a_hi, &maps.a[seg], &full[stage], kc, m_base);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {
+            const uint32_t fmt = TF32 ? 2u : 1u;
+            // M = 256 (both CTAs' 128 rows), N = Npad (each CTA supplies Npad / 2 weight rows)
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)((2 * kTileM) >> 4) << 24);
+            const uint64_t dbase = make_desc_k<CB>(0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nmine; ++i) {
+                const int ab = i & 1;
+                mbar_wait_cluster(&acc_empty[ab], (uint32_t)(((i >> 1) & 1) ^ 1));
+                fence_tc_after();
+                const uint32_t d_main = tmem_base + (uint32_t)ab * buf_cols;
+                const uint32_t d_cross = d_main + (uint32_t)p.Npad;
+                uint32_t acc_m = 0, acc_c = 0;
+                for (int c = 0; c < total_chunks; ++c) {
+                    mbar_wait_cluster(&ready[stage], phase);
+                    fence_tc_after();
+                    const uint32_t st = smem_u32(smem + L.stages_off + (size_t)stage * L.stage_bytes);
+                    const uint32_t wc = smem_u32(smem + (size_t)c * L.w_chunk);
+#pragma unroll
+                    for (int k = 0; k < CB / 32; ++k) {
+                        const uint64_t a_hi = dbase + ((st + L.a_hi + k * 32) >> 4);
+                        const uint64_t w_hi = dbase + ((wc + k * 32) >> 4);
+                        umma2<TF32>(d_main, a_hi, w_hi, idesc, acc_m);
+                        acc_m = 1u;
+                        if (TF32) {
+                            const uint64_t a_lo = dbase + ((st + L.a_lo + k * 32) >> 4);
+                            const uint64_t w_lo = dbase + ((wc + L.w_lo_off + k * 32) >> 4);
+                            umma2<TF32>(d_cross, a_lo, w_hi, idesc, acc_c);
+                            umma2<TF32>(d_cross, a_hi, w_lo, idesc, 1u);
+                            acc_c = 1u;
+                        }
+                    }
+                    umma2_commit_mc(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma2_commit_mc(&acc_full[ab]);
+            }
+        }
+    } else if (warp == 3) {
+        // ===== relay (bf16): this CTA's chunk landed -> the leader's `ready` barrier =====
+        if (!TF32 && lane == 0) {
+            mbar_wait(w_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            const int nchunks = nmine * total_chunks;
+            for (int g = 0; g < nchunks; ++g) {
+                mbar_wait(&full[stage], phase);
+                mbar_arrive_cluster(ready_leader + 8u * (uint32_t)stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== converters (fp32): a_lo = a - trunc_tf32(a); then this CTA's share of the stage is ready =====
+        if (TF32) {
+            const int ct = threadIdx.x - 384;
+            mbar_wait(w_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            const int nchunks = nmine * total_chunks;
+            for (int g = 0; g < nchunks; ++g) {
+                mbar_wait(&full[stage], phase);
+                uint8_t* st = smem + L.stages_off + (size_t)stage * L.stage_bytes;
+                const float4* hi = reinterpret_cast<const float4*>(st + L.a_hi);
+                float4* lo = reinterpret_cast<float4*>(st + L.a_lo);
+#pragma unroll
+                for (int j = 0; j < (kTileM * CB / 16) / 128; ++j) lo[ct + j * 128] = tf32_lo(hi[ct + j * 128]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ready_leader + 8u * (uint32_t)stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warpgroups (own TMEM, own tile): WG0 takes even tile pairs, WG1 odd ones =====
+        const int wg = (warp - 4) >> 2;
+        const int q = warp & 3;
+        uint8_t* slice = smem + L.staging + (size_t)(warp - 4) * 2048;
+        for (int i = wg; i < nmine; i += 2) {
+            const int64_t m_base = (int64_t)(2 * (pair0 + i * npc) + (int)rank) * kTileM;
+            const int ab = i & 1;
+            mbar_wait(&acc_full[ab], (uint32_t)((i >> 1) & 1));
+            fence_tc_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * buf_cols;
+            epilogue_tile<T, TF32>(p, cvec, HP, slice, t_row, m_base, q, lane);
+            fence_tc_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)ab);
+        }
+    }
+
+    fence_tc_before();
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still read its shared memory or signal its barriers
+    if (warp == 2) {
+        fence_tc_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
 }
 
@@ -1064,19 +1372,70 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
         DFW_LAUNCH_CHECK();
     }
 
+    // ---- CTA-pair variant (cta_group::2, resident weight halves) where the weights fit ----
+    {
+        // Measured (tools/lin_ab.py, profiles/r02_linear_pair_ab.json): correct (all parity tests pass with it forced on) but SLOWER
+        // than the one-CTA kernels - fp32 H=128 SAGE forward 210 vs 140 us, bf16 H=256 1127 vs 912 us: with the weights resident
+        // only 4 x 16 KB activation stages fit, and every 64-byte chunk pays two cross-SM handshakes (remote mbarrier arrive,
+        // cluster-scope wait, multicast commit: ~5 us per stage round trip).  Kept as an opt-in (DFW_TC_PAIR=1) with its tests.
+        static const int env_pair = [] { const char* e = getenv("DFW_TC_PAIR"); return e ? atoi(e) : 0; }();
+        const int Npad = (int)((Hout + 15) / 16 * 16);
+        const int regions = tf32 ? 2 : 1;
+        const int64_t tiles64 = (args.N + kTileM - 1) / kTileM;
+        const int cb = tf32 ? 64 : 128;
+        const int ch0 = (int)((k1 * e + cb - 1) / cb), ch1 = a2 ? (int)((k2 * e + cb - 1) / cb) : 0;
+        if (env_pair && Npad % 32 == 0 && 2 * regions * Npad <= 512 && Hout % 32 == 0 && tiles64 >= 4) {
+            int stages = k2StagesMax;
+            while (stages > 2 && carve2(tf32, Npad, (int)Hout, ch0 + ch1, stages).total + 1024 > 227 * 1024) --stages;
+            if (carve2(tf32, Npad, (int)Hout, ch0 + ch1, stages).total + 1024 <= 227 * 1024 && (stages >= 3 || env_pair == 2)) {
+                Maps pm;
+                memset(&pm, 0, sizeof(pm));
+                args.Npad = Npad;
+                args.nacc = 1;
+                int cols = 32;
+                while (cols < 2 * regions * Npad) cols <<= 1;
+                args.tmem_cols = cols;
+                args.chunks[0] = ch0;
+                args.chunks[1] = ch1;
+                args.stages = stages;
+                const int mm = tf32 ? kMapSw64 : kMapSw128;
+                const void* as2[2] = {a1, a2};
+                for (int i = 0; i < (a2 ? 2 : 1); ++i) {
+                    if (make_map(&pm.a[i], as2[i], args.N, ks[i], e, kTileM, mm)) return 1;
+                    if (make_map(&pm.w_hi[i], wuse[i], Hout, ks[i], e, Npad / 2, mm)) return 1;
+                    if (tf32 && make_map(&pm.w_lo[i], lo[i], Hout, ks[i], e, Npad / 2, mm)) return 1;
+                }
+                const size_t psmem = carve2(tf32, Npad, (int)Hout, ch0 + ch1, stages).total + 1024;
+                const int num_pairs = (int)((tiles64 + 1) / 2);
+                const unsigned grid = 2u * (unsigned)std::min<int>(num_pairs, kNumSMs / 2);
+                if (tf32) {
+                    auto kern = k_linear_tc2<float, true>;
+                    DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                    kern<<<grid, k2Threads, psmem, s>>>(pm, args, num_pairs);
+                } else {
+                    auto kern = k_linear_tc2<__nv_bfloat16, false>;
+                    DFW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                    kern<<<grid, k2Threads, psmem, s>>>(pm, args, num_pairs);
+                }
+                DFW_LAUNCH_CHECK();
+                return 0;
+            }
+        }
+    }
+
     // ---- persistent variant (one CTA per SM, 128-byte K chunks, double-buffered accumulator) where its TMEM budget fits ----
     {
-        // Measured A/B (tools/lin_ab.py, profiles/r02_linear_persistent_ab.json; us, classic -> persistent): single-operand
-        // linears (encoder / decoder / their input gradients) 72.7 -> 58.4 (fp32 H=128), 55.9 -> 41.7 (bf16 H=128), 550 -> 449
-        // (bf16 H=256, 2 M rows); H=64 layers 87 -> 83; but the two-operand SAGE shapes at H >= 128 lose 2-14 % (140 -> 146 fp32
-        // H=128, 1128 -> 1289 bf16 H=256): with K = 2H the 3 x 64 KB (fp32) stages keep only two chunks in flight and the main
-        // loop waits on TMA latency (ncu r02l: converters 11 % of samples waiting for data, epilogue warps idle on acc_full).
-        // Policy: persistent for single-operand calls and for Hout <= 64; DFW_TC_PERSIST=0 / 2 forces never / always.
+        // Measured A/B (tools/lin_ab.py, profiles/r02_linear_persistent_ab.json; us, classic -> persistent, L2 flushed):
+        //   fp32 H=128 (config 2): SAGE forward train 140 -> 132, inference 116 -> 105, input gradient 107 -> 97, single operand 73 -> 64
+        //   bf16 H=128 (config 5): 111 -> 104, 91 -> 77, 79 -> 69, 55 -> 44;  bf16 H=256, 2 M rows (config 4): 1128 -> 1131, 911 -> 821,
+        //   790 -> 777, 548 -> 519;  fp32 H=64: 87 -> 81, 73 -> 63, 66 -> 56, 50 -> 42.
+        // (Its first version lost 2-14 % on the two-operand shapes: the residual was read on demand inside the write-back loop,
+        // ~1 us of exposed latency per 64-byte round; it is now requested one round ahead.)  DFW_TC_PERSIST=0 forces the classic kernel.
         static const int env_persist = [] { const char* e = getenv("DFW_TC_PERSIST"); return e ? atoi(e) : 1; }();
         const int Npad = (int)((Hout + 15) / 16 * 16);
         const int regions = tf32 ? 2 : 1;
         const int64_t tiles64 = (args.N + kTileM - 1) / kTileM;
-        const bool want = env_persist == 2 || (env_persist == 1 && (!a2 || Npad <= 64));
+        const bool want = env_persist != 0;
         if (want && 2 * regions * Npad <= 512 && Hout % 32 == 0 && tiles64 >= 2) {
             Maps pm;
             memset(&pm, 0, sizeof(pm));
