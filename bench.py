@@ -391,6 +391,51 @@ def aggregation_cfg4(device, pk, iters=20):
     return out
 
 
+def partitioned_cfg4(device, rank, world, iters=5):
+    """the config-4 mesh (2 M nodes, H = 256, L = 3, bf16, eval) as ONE forward partitioned over the ranks -
+    1-D node partition in k-d order, one NCCL all-to-all of halo rows per SAGE layer (gnn/partition.py).  STRONG scaling of a
+    single mesh (the training arms of this line are weak scaling); time = max over ranks."""
+    import torch.distributed as dist
+
+    from deep_fem_uav_wing.gnn.model import GraphSAGEModel
+    from deep_fem_uav_wing.gnn.partition import PartitionedMeshInference
+
+    ei, pos_n, n = cfg4_lattice_device(CFG4_DIMS, device, "native")
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, device=device, generator=torch.Generator(device=device).manual_seed(2)), dim=1)
+    feats = torch.cat([pos_n, nrm, torch.full((n, 4), 0.5, device=device)], dim=1).contiguous()
+    torch.manual_seed(0)
+    model = GraphSAGEModel(10, 256, 1, 3).to(device).eval().set_compute_dtype(torch.bfloat16)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    pm = PartitionedMeshInference(model, feats, ei)
+    torch.cuda.synchronize(device)
+    prep_ms = (time.perf_counter() - t0) * 1e3
+    del ei, feats, nrm
+    for _ in range(2):
+        pm()
+    ts = []
+    for _ in range(iters):
+        dist.barrier()
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = pm()
+        b.record()
+        torch.cuda.synchronize(device)
+        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ts.append(float(ms.item()))
+    ts.sort()
+    halo = torch.tensor([float(pm.halo_rows)], device=device)
+    dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+    res = {"ms": round(ts[len(ts) // 2], 3), "nodes_per_sec": n / (ts[len(ts) // 2] * 1e-3), "N": n, "ranks": world, "hidden": 256, "layers": 3, "dtype": "bf16",
+           "max_halo_rows_per_rank": int(halo.item()), "rows_per_rank": pm.part.n_own, "one_time_partitioning_ms": round(prep_ms, 1),
+           "scaling": "strong (one mesh)", "exchange": "all_to_all_single of halo rows per SAGE layer (NCCL)", "finite": bool(torch.isfinite(out).all())}
+    del pm, model
+    torch.cuda.empty_cache()
+    return res
+
+
 # --------------------------------------------------------------------------------------------
 # BASELINE.json config 5: design-screening batch inference, case list sharded over the ranks, no communication
 # --------------------------------------------------------------------------------------------
@@ -729,12 +774,14 @@ def main():
                "nodes_per_batch": int(tres[0].x.shape[0]), "edges_per_batch": int(tres[0].edge_index.shape[1]),
                "what": "same training step, device-resident, on 4 x 50k-node TET-lattice meshes (degree ~14), 2 batches cycled"}
 
-    # ---- config 5 (every N) and config 4's aggregation roofline (N = 1) --------------------------------------------------
-    cfg5 = agg4 = None
+    # ---- config 5 (every N), config 4's aggregation roofline (N = 1), config 4 partitioned over the ranks (N > 1) ---------
+    cfg5 = agg4 = part4 = None
     if not args.no_extras:
         cfg5 = cfg5_block(device, rank, world, dist_on)
         if world == 1:
             agg4 = aggregation_cfg4(device, pk)
+        else:
+            part4 = partitioned_cfg4(device, rank, world)
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
@@ -756,7 +803,7 @@ def main():
             "infer": infer,
             "aggregation": {"kernel": "dfw_sage_aggregate (forward mean, this workload)", "achieved_GBps": kernels.get("aggregate", {}).get("achieved_GBps"),
                             "hbm_frac": kernels.get("aggregate", {}).get("hbm_frac")},
-            "aggregation_cfg4": agg4, "cfg5": cfg5, "tet_batch": tet, "parity": gates,
+            "aggregation_cfg4": agg4, "partitioned_cfg4": part4, "cfg5": cfg5, "tet_batch": tet, "parity": gates,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         }
         emit(line)

@@ -12,8 +12,9 @@ latency-bound over NVLink/NVSwitch.  Design:
 * ``finish()`` waits for the buckets before the optimizer step;
 * ``scale_loss`` reproduces the single-process loss of the union batch exactly: the reference's
   ``MaskedMSELoss`` is a mean over the masked nodes of the WHOLE batch (``model.py:151``), so each
-  rank back-propagates its SUM of squared errors (``loss_r * count_r``), the counts are all-reduced
-  asynchronously next to the gradients, and ``finish()`` divides by the total count.
+  rank back-propagates its SUM of squared errors (``loss_r * count_r``); the rank's masked count rides in
+  one extra element of the FIRST bucket that is reduced (no collective of its own), and ``finish()``
+  divides the summed gradients by the summed count.
 Works with any backend (NCCL on GPUs; gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -38,17 +39,22 @@ class MeshDataParallel(nn.Module):
         order = list(reversed(params))
         sizes = [p.numel() for p in order]
         total = sum(sizes)
-        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        # one extra element right behind the first parameter in backward order: this rank's masked count (see scale_loss)
+        self.flat = torch.zeros(total + 1, dtype=dt, device=dev)
         per = (total + num_buckets - 1) // max(num_buckets, 1)
         self.buckets: list[tuple[int, int]] = []
         self._bucket_of: dict[int, int] = {}
         self._pending: list[int] = []
         off, start, b = 0, 0, 0
+        self._count_slot = None
         for p, n in zip(order, sizes):
             p.grad = self.flat[off:off + n].view_as(p)
             self._bucket_of[id(p)] = b
             off += n
-            if off - start >= per or off == total:
+            if self._count_slot is None:
+                self._count_slot = off
+                off += 1
+            if off - start >= per or off == total + 1:
                 self.buckets.append((start, off))
                 start, b = off, b + 1
         self._remaining = [0] * len(self.buckets)
@@ -56,7 +62,7 @@ class MeshDataParallel(nn.Module):
         for p in order:
             self._count[self._bucket_of[id(p)]] += 1
         self._handles: list = []
-        self._tot, self._tot_handle = None, None
+        self._scaled = False
         self._reset()
         if self.world > 1:
             # identical initial weights on every rank
@@ -94,9 +100,10 @@ class MeshDataParallel(nn.Module):
         while the backward runs (a blocking all-reduce here was a synchronisation point of all ranks mid-step)."""
         if self.world == 1:
             return loss
-        self._tot = count.detach().clone().float().reshape(1)
-        self._tot_handle = dist.all_reduce(self._tot, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-        return loss * count.detach().float().reshape(())
+        c = count.detach().float().reshape(1)
+        self.flat[self._count_slot:self._count_slot + 1].copy_(c)  # travels with the first gradient bucket
+        self._scaled = True
+        return loss * c.reshape(())
 
     def finish(self):
         """Call after ``backward()`` and before ``optimizer.step()``."""
@@ -110,10 +117,9 @@ class MeshDataParallel(nn.Module):
                         self._launch(b)
             for h in self._handles:
                 h.wait()
-            if self._tot_handle is not None:  # gradients of per-rank SUMS -> gradient of the union-batch mean
-                self._tot_handle.wait()
-                self.flat.div_(self._tot.clamp_min(1.0))
-                self._tot_handle = None
+            if self._scaled:  # gradients of per-rank SUMS -> gradient of the union-batch mean
+                self.flat.div_(self.flat[self._count_slot:self._count_slot + 1].clamp_min(1.0))
+                self._scaled = False
             else:  # scale_loss was not used: plain average of the ranks' gradients
                 self.flat.div_(self.world)
         self._reset()

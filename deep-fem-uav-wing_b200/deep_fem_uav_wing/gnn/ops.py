@@ -319,6 +319,22 @@ def aggregate(rowptr, col, row_scale, x, addend=None):
     return out
 
 
+def aggregate_rows(rowptr, col, row_scale, x_ext, n_rows: int):
+    """Mean / sum aggregation whose SOURCE tensor has more rows than there are output rows: ``rowptr`` describes ``n_rows``
+    destination rows, ``col`` indexes ``x_ext [n_ext, H]`` (own rows followed by halo rows: ``gnn/partition.py``)."""
+    _require_cuda(x_ext, "x")
+    x_ext = x_ext.contiguous()
+    H = x_ext.shape[1]
+    E = col.shape[0]
+    out = torch.empty(n_rows, H, dtype=x_ext.dtype, device=x_ext.device)
+    amin = (n_rows + x_ext.shape[0]) * H * _esz(x_ext) + 4 * E + 4 * (n_rows + 1)
+    with torch.cuda.device(x_ext.device), _prof("aggregate", amin):
+        check(lib.dfw_sage_aggregate(rowptr.data_ptr(), _ptr(col) if E else None, _ptr(row_scale), x_ext.data_ptr(), None, out.data_ptr(), n_rows, E, H,
+                                     _dt(x_ext), _stream(x_ext)))
+    LAUNCH_COUNTER["kernels"] += 1
+    return out
+
+
 def aggregate_scaled(rowptr, col, src_scale, x, label="aggregate_bwd"):
     """``out[i] = sum_k src_scale[col[k]] * x[col[k]]`` (``dfw_sage_aggregate_scaled``)."""
     _require_cuda(x, "x")
