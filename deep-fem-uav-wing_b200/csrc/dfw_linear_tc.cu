@@ -667,7 +667,7 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* cvec, 
     };
     auto load_acc = [&](int c0, float* v) {  // hi*hi + cross terms, summed in round-to-nearest fp32 (see tmem_combine)
         tmem_ld32(t_row + c0, v);
-        if (TF32) {
+        if (TF32 && p.nacc != 0) {  // (nacc == 0: dev probe, every product accumulated in one region)
             float w[32];
             tmem_ld32(t_row + p.Npad + c0, w);
 #pragma unroll
@@ -895,8 +895,15 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
                         const uint64_t w_hi = dbase + ((st + L.w_hi + k * 32) >> 4);
                         if (TF32) {
                             const uint64_t a_lo = dbase + ((st + L.a_lo + k * 32) >> 4);
-                            umma<TF32>(d_tmem, a_hi, w_hi, idesc2, accumulate);                   // main = a_hi.w_hi | cross = a_hi.w_lo
-                            umma<TF32>(d_tmem + (uint32_t)p.Npad, a_lo, w_hi, idesc, 1u);         // cross += a_lo.w_hi
+                            if (p.nacc != 0) {
+                                umma<TF32>(d_tmem, a_hi, w_hi, idesc2, accumulate);                   // main = a_hi.w_hi | cross = a_hi.w_lo
+                                umma<TF32>(d_tmem + (uint32_t)p.Npad, a_lo, w_hi, idesc, 1u);         // cross += a_lo.w_hi
+                            } else {  // dev probe (DFW_TC_MERGE=1): all three products into ONE accumulator
+                                const uint64_t w_lo = dbase + ((st + L.w_lo + k * 32) >> 4);
+                                umma<TF32>(d_tmem, a_lo, w_hi, idesc, accumulate);
+                                umma<TF32>(d_tmem, a_hi, w_lo, idesc, 1u);
+                                umma<TF32>(d_tmem, a_hi, w_hi, idesc, 1u);
+                            }
                         } else {
                             umma<TF32>(d_tmem, a_hi, w_hi, idesc, accumulate);
                         }
@@ -1440,7 +1447,8 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
             Maps pm;
             memset(&pm, 0, sizeof(pm));
             args.Npad = Npad;
-            args.nacc = 1;
+            static const int env_merge = [] { const char* e = getenv("DFW_TC_MERGE"); return e ? atoi(e) : 0; }();  // dev probe
+            args.nacc = env_merge ? 0 : 1;
             int cols = 32;
             while (cols < 2 * regions * Npad) cols <<= 1;
             args.tmem_cols = cols;

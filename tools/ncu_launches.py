@@ -15,6 +15,8 @@ for r in rows[hi + 1:]:
         continue
     m = re.search(r"(k_[a-z0-9_]+|at::native::[a-zA-Z_]+|[a-zA-Z_]+_kernel[a-zA-Z_]*)", r[kn])
     name = m.group(1) if m else r[kn][:40]
+    if r[mv].strip().lower() == "nan":  # kernels recorded while a CUDA graph is being captured do not run
+        continue
     v = float(r[mv].replace(",", ""))
     v = v / 1000 if r[mu] == "ns" else (v * 1000 if r[mu] == "ms" else v)
     d = agg.setdefault(name, [0, 0.0])
