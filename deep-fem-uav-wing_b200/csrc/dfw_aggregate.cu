@@ -16,6 +16,7 @@
 //    instruction-issue bound, not bandwidth bound, on a naive kernel (profiles/r01_ncu_*_v1.csv).
 // Roofline: HBM.  Algorithmic bytes per launch  A_min = 2*N*H*b + 4*E + 4*(N+1)  (DESIGN.md).
 #include <algorithm>
+#include <cstdlib>
 
 #include "dfw_common.cuh"
 
@@ -365,29 +366,38 @@ inline int pick_rows_per_group(int64_t N, int64_t E, int lanes, int groups, int 
 // and 32 warps x two half batches (750 us): thread-level parallelism hides the per-block prologue best.
 constexpr int kAggThreads = 1024;
 
-template <typename T, int LANES, int VPL>
-int launch(const int32_t* rowptr, const int32_t* col, const float* row_scale, const float* src_scale, const void* x,
-           const void* addend, void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
+template <typename T, int LANES, int VPL, int THREADS, bool PIPE>
+int launch_v(const int32_t* rowptr, const int32_t* col, const float* row_scale, const float* src_scale, const void* x,
+             const void* addend, void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
     constexpr int GROUPS = 32 / LANES;
-    const int R = pick_rows_per_group(N, E, LANES, GROUPS, kAggThreads);
-    const int64_t chunk_rows = (int64_t)R * GROUPS * (kAggThreads / 32);
+    const int R = pick_rows_per_group(N, E, LANES, GROUPS, THREADS);
+    const int64_t chunk_rows = (int64_t)R * GROUPS * (THREADS / 32);
     const int64_t chunks = (N + chunk_rows - 1) / chunk_rows;
     const int64_t blocks = std::min<int64_t>(chunks, kNumSMs);
     if (blocks == 0) return 0;
     const bool exact = nvec == LANES * VPL;
-#define DFW_AGG_GO(A, X, S)                                                                                                  \
-    k_aggregate<T, LANES, VPL, A, X, S, kAggThreads, 1, false><<<(unsigned)blocks, kAggThreads, 0, s>>>(                         \
+#define DFW_AGG_GO(A, X, S, P)                                                                                               \
+    k_aggregate<T, LANES, VPL, A, X, S, THREADS, 1, P><<<(unsigned)blocks, THREADS, 0, s>>>(                                   \
         rowptr, col, row_scale, src_scale, (const T*)x, (const T*)addend, (T*)out, N, nvec, R)
-    if (src_scale) {  // (the scaled gather is only used without an addend: backward of the mean)
-        if (exact) DFW_AGG_GO(false, true, true); else DFW_AGG_GO(false, false, true);
+    if (src_scale) {  // (the scaled gather is only used without an addend: backward of the mean; its scales live in one register set)
+        if (exact) DFW_AGG_GO(false, true, true, false); else DFW_AGG_GO(false, false, true, false);
     } else if (exact) {
-        if (addend) DFW_AGG_GO(true, true, false); else DFW_AGG_GO(false, true, false);
+        if (addend) DFW_AGG_GO(true, true, false, PIPE); else DFW_AGG_GO(false, true, false, PIPE);
     } else {
-        if (addend) DFW_AGG_GO(true, false, false); else DFW_AGG_GO(false, false, false);
+        if (addend) DFW_AGG_GO(true, false, false, PIPE); else DFW_AGG_GO(false, false, false, PIPE);
     }
 #undef DFW_AGG_GO
     DFW_LAUNCH_CHECK();
     return 0;
+}
+
+template <typename T, int LANES, int VPL>
+int launch(const int32_t* rowptr, const int32_t* col, const float* row_scale, const float* src_scale, const void* x,
+           const void* addend, void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
+    static const int variant = [] { const char* e = getenv("DFW_AGG_VARIANT"); return e ? atoi(e) : 0; }();  // dev probe
+    if (variant == 1) return launch_v<T, LANES, VPL, 512, true>(rowptr, col, row_scale, src_scale, x, addend, out, N, E, nvec, s);
+    if (variant == 2) return launch_v<T, LANES, VPL, 768, false>(rowptr, col, row_scale, src_scale, x, addend, out, N, E, nvec, s);
+    return launch_v<T, LANES, VPL, kAggThreads, false>(rowptr, col, row_scale, src_scale, x, addend, out, N, E, nvec, s);
 }
 
 template <typename T>

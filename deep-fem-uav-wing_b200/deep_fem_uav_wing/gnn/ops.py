@@ -360,7 +360,8 @@ class AggPlan:
     plan_rec: torch.Tensor
     plan_slot: torch.Tensor
     status: torch.Tensor          # uint64-as-int64 [2] on the device: [0] max edges of a block, [1] total staged rows
-    usable: bool | None = None    # resolved by ``check()`` (one 16-byte D2H read)
+    usable: bool | None = None    # resolved by ``check()`` (one 16-byte D2H read): the plan is structurally valid
+    profitable: bool = True       # cleared by get_inference_graph for low-degree graphs, where the gather kernel is faster
     staged_rows_per_row: float | None = None
 
     def check(self) -> bool:
@@ -468,8 +469,10 @@ def locality_order(pos: torch.Tensor, edge_index: torch.Tensor, leaf: int = 128,
 
 
 TC_AGG_WIDTHS = (64, 128, 256)
-TC_AGG_MIN_NODES = 1 << 18        # below this the gather kernel is launch / L2 bound anyway and the plan is not worth building
+TC_AGG_MIN_NODES = 1 << 17        # below this the gather kernel is launch / L2 bound anyway and the plan is not worth building
 TC_AGG_REORDER_ABOVE = 3.2        # staged rows per output row above which a k-d relabelling is tried
+TC_AGG_MIN_REUSE = 3.0            # edges per staged row below which the gather kernel wins (measured, tools/aggtc_small.py: surface
+                                  # meshes, degree 6 / 3.0 staged = 2.0: gather 46 us vs block 54 us; tet, 13 / 3.35 = 3.9: 68 vs 55 us)
 
 
 def aggregate_mean(graph: "CSRGraph", x):
@@ -477,7 +480,7 @@ def aggregate_mean(graph: "CSRGraph", x):
     qualify (bf16, H in 64/128/256), the gather kernel otherwise.  Both are deterministic; they differ by the association
     order of fp32 additions only."""
     pl = graph.plan
-    if pl is not None and pl.usable and x.dtype == torch.bfloat16 and x.shape[1] in TC_AGG_WIDTHS:
+    if pl is not None and pl.usable and pl.profitable and x.dtype == torch.bfloat16 and x.shape[1] in TC_AGG_WIDTHS:
         return aggregate_tc(pl, graph.inv_deg, x, graph.num_edges)
     return aggregate(graph.rowptr, graph.col, graph.inv_deg, x)
 
@@ -523,6 +526,9 @@ def get_inference_graph(edge_index: torch.Tensor, num_nodes: int, pos: torch.Ten
             order = torch.empty_like(new_id)
             order[new_id] = torch.arange(num_nodes, device=new_id.device)
             ig = InferenceGraph(g2, new_id, order, g.plan.staged_rows_per_row, g2.plan.staged_rows_per_row)
+    pl = ig.graph.plan
+    if pl is not None and pl.usable and ig.graph.num_edges / max(num_nodes, 1) < TC_AGG_MIN_REUSE * pl.staged_rows_per_row:
+        pl.profitable = False  # low-degree graph: every staged row would serve too few edges; aggregate_mean takes the gather kernel
     _INF_CACHE[key] = ig
     while len(_INF_CACHE) > 4:
         _INF_CACHE.popitem(last=False)
