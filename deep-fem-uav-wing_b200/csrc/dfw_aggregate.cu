@@ -370,7 +370,8 @@ template <typename T, int LANES, int VPL, int THREADS, bool PIPE>
 int launch_v(const int32_t* rowptr, const int32_t* col, const float* row_scale, const float* src_scale, const void* x,
              const void* addend, void* out, int64_t N, int64_t E, int nvec, cudaStream_t s) {
     constexpr int GROUPS = 32 / LANES;
-    const int R = pick_rows_per_group(N, E, LANES, GROUPS, THREADS);
+    static const int env_r = [] { const char* e = getenv("DFW_AGG_R"); return e ? atoi(e) : 0; }();  // dev probe
+    const int R = env_r > 0 ? std::min(env_r, LANES - 1) : pick_rows_per_group(N, E, LANES, GROUPS, THREADS);
     const int64_t chunk_rows = (int64_t)R * GROUPS * (THREADS / 32);
     const int64_t chunks = (N + chunk_rows - 1) / chunk_rows;
     const int64_t blocks = std::min<int64_t>(chunks, kNumSMs);

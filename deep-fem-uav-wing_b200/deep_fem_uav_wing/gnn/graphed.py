@@ -54,7 +54,12 @@ class GraphedTrainStep:
             self.optimizer.zero_grad(set_to_none=True)
         return self._step(x, edge_index, y, mask)
 
-    def __call__(self, x, edge_index, y, mask):
+    def __call__(self, x, edge_index, y, mask, graph=None):
+        """``graph``: the batch's prebuilt ``ops.CSRGraph`` with its transpose (``DataLoader(build_graph=True)`` builds it on the
+        copy stream under the previous step): the captured step then starts at the encoder - the CSR arrays are copied into
+        static buffers like ``x`` - instead of rebuilding the CSR from ``edge_index`` inside the graph."""
+        if graph is not None and graph.rowptr_t is not None:
+            return self._call_prebuilt(x, graph, y, mask)
         key = (int(x.shape[0]), int(edge_index.shape[1]), x.dtype)
         entry = self._graphs.get(key)
         if entry is None:
@@ -71,6 +76,47 @@ class GraphedTrainStep:
         sm.copy_(mask, non_blocking=True)
         g.replay()
         ops.LAUNCH_COUNTER["kernels"] += self.kernels_per_replay
+        return sloss
+
+    def _call_prebuilt(self, x, graph, y, mask):
+        key = (int(x.shape[0]), int(graph.num_edges), x.dtype, "csr")
+        entry = self._graphs.get(key)
+        if entry is None:
+            n = self._seen.get(key, 0)
+            if n < self.eager_steps or len(self._graphs) >= self.max_graphs:
+                self._seen[key] = n + 1
+                return self._eager(x, graph, y, mask)
+            # static copies of the batch and of its CSR (forward and transposed); the captured step reads only these
+            sx, sy, sm = (torch.empty_like(t) for t in (x, y, mask))
+            sg = ops.CSRGraph(None, graph.num_nodes, graph.num_edges, torch.empty_like(graph.rowptr), torch.empty_like(graph.col),
+                              torch.empty_like(graph.inv_deg), None, None)
+            sg.rowptr_t, sg.col_t = torch.empty_like(graph.rowptr_t), torch.empty_like(graph.col_t)
+            for d, s_ in ((sx, x), (sy, y), (sm, mask), (sg.rowptr, graph.rowptr), (sg.col, graph.col), (sg.inv_deg, graph.inv_deg),
+                          (sg.rowptr_t, graph.rowptr_t), (sg.col_t, graph.col_t)):
+                d.copy_(s_)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            if self.ddp is None:
+                self.optimizer.zero_grad(set_to_none=True)
+            k0 = ops.LAUNCH_COUNTER["kernels"]
+            with torch.cuda.graph(g, pool=self._pool, capture_error_mode="thread_local"):
+                sloss = self._step(sx, sg, sy, sm)
+            kernels = ops.LAUNCH_COUNTER["kernels"] - k0
+            if self._pool is None:
+                self._pool = g.pool()
+            entry = (g, sx, sy, sm, sg, sloss, kernels)
+            self._graphs[key] = entry
+        g, sx, sy, sm, sg, sloss, kernels = entry
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(y, non_blocking=True)
+        sm.copy_(mask, non_blocking=True)
+        sg.rowptr.copy_(graph.rowptr, non_blocking=True)
+        sg.col.copy_(graph.col, non_blocking=True)
+        sg.inv_deg.copy_(graph.inv_deg, non_blocking=True)
+        sg.rowptr_t.copy_(graph.rowptr_t, non_blocking=True)
+        sg.col_t.copy_(graph.col_t, non_blocking=True)
+        g.replay()
+        ops.LAUNCH_COUNTER["kernels"] += kernels
         return sloss
 
     def capture_resident(self, x, edge_index, y, mask):

@@ -131,7 +131,8 @@ class DataLoader:
     ``drop_last``."""
 
     def __init__(self, dataset: Sequence[Data], batch_size: int = 1, shuffle: bool = False, drop_last: bool = False,
-                 device=None, rank: int = 0, world_size: int = 1, seed: int | None = None, keys: Iterable[str] | None = None):
+                 device=None, rank: int = 0, world_size: int = 1, seed: int | None = None, keys: Iterable[str] | None = None,
+                 build_graph: bool = False):
         self.dataset = dataset
         self.batch_size = int(batch_size)
         self.shuffle = shuffle
@@ -143,6 +144,12 @@ class DataLoader:
         self.seed = seed
         self.epoch = 0
         self.keys = tuple(keys) if keys is not None else None
+        # build_graph: the prefetch worker also builds the batch's CSR (+ its transpose) ON THE COPY STREAM, right behind the H2D
+        # copies, and attaches it as ``batch.graph`` (registered for ``batch.edge_index``): the graph construction of batch i+1
+        # then runs under the compute of batch i instead of at the head of its step.  Off by default: on the config-2 step it
+        # measured no gain (2.74 vs 2.75 ms; the small build kernels only find room between the step's full-chip kernels) and the
+        # per-batch allocations on a second stream make the caching allocator grow for the first epochs (tools/e2e_probe.py).
+        self.build_graph = bool(build_graph)
         self._copy_stream = None
         self._pinned = None
 
@@ -286,6 +293,12 @@ class DataLoader:
                     items = [self._pinned_item(i) for i in chunk]
                     with torch.cuda.stream(cs):
                         out = self._device_collate(items, dev)
+                        if self.build_graph and getattr(out, "edge_index", None) is not None:
+                            from . import ops
+
+                            g = ops.get_graph(out.edge_index, int(out.x.shape[0]))
+                            g.transpose()
+                            out.graph = g
                         ev = torch.cuda.Event()
                         ev.record(cs)
                     q.put((out, ev))
@@ -308,6 +321,11 @@ class DataLoader:
                 for v in batch.__dict__.values():
                     if isinstance(v, torch.Tensor) and v.is_cuda:
                         v.record_stream(cur)
+                g = batch.__dict__.get("graph")
+                if g is not None:  # the CSR arrays were allocated on the copy stream too
+                    for v in (g.rowptr, g.col, g.inv_deg, g.rowptr_t, g.col_t, g.status, g.status_t):
+                        if isinstance(v, torch.Tensor) and v.is_cuda:
+                            v.record_stream(cur)
                 yield batch
         finally:
             stop.set()

@@ -442,3 +442,47 @@ def test_degenerate_graphs_match_oracle_forward_and_backward():
                 assert q.grad.abs().max().item() < 1e-12, (name, k)
             else:
                 assert rel_l2(q.grad.cpu(), qr.grad) < 2 * TOL_FP32, (name, k, rel_l2(q.grad.cpu(), qr.grad))
+
+
+@pytest.mark.gpu
+def test_loader_prebuilt_graph_and_graphed_step_follow_the_eager_trajectory():
+    """DataLoader(build_graph=True) builds every batch's CSR (+ transpose) on its copy stream and GraphedTrainStep(graph=...) replays
+    a CUDA graph that starts from those arrays: losses and parameters must follow the plain eager loop on the same batches."""
+    from deep_fem_uav_wing.gnn import ops, synth
+    from deep_fem_uav_wing.gnn.graphed import GraphedTrainStep
+    from deep_fem_uav_wing.gnn.loader import Data, DataLoader
+
+    GraphSAGEModel, MaskedMSELoss, _, _ = _models()
+    datas = []
+    for s in range(8):  # same grid -> same (N, E): one captured graph
+        m = synth.surface_tri_wing(2400, seed=s)
+        datas.append(Data(x=torch.from_numpy(m["x"]), edge_index=torch.from_numpy(m["edge_index"]), y=torch.from_numpy(m["y"]),
+                          loss_mask=torch.from_numpy(m["loss_mask"])))
+
+    def run(prebuilt):
+        torch.manual_seed(0)
+        model = GraphSAGEModel(10, 64, 1, 2, dropout=0.0).cuda().train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=True)
+        crit = MaskedMSELoss()
+        losses = []
+        if prebuilt:
+            step = GraphedTrainStep(model, crit, opt, eager_steps=1)
+            for b in DataLoader(datas, batch_size=2, shuffle=False, device="cuda", build_graph=True):
+                assert b.graph is not None and b.graph.rowptr_t is not None
+                assert ops.get_graph(b.edge_index, b.x.shape[0]) is b.graph  # registered for the batch's edge_index
+                losses.append(step(b.x, b.edge_index, b.y, b.loss_mask, graph=b.graph).item())
+            assert any(len(k) == 4 for k in step._graphs), "the prebuilt-CSR step was never captured"
+        else:
+            for b in DataLoader(datas, batch_size=2, shuffle=False, device="cuda"):
+                opt.zero_grad(set_to_none=True)
+                loss = crit(model(b.x, b.edge_index, b.batch), b.y, b.loss_mask)
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+        return losses, model
+
+    eager, m_e = run(False)
+    pre, m_p = run(True)
+    np.testing.assert_allclose(pre, eager, rtol=1e-5)
+    for (k, a), b in zip(m_p.named_parameters(), m_e.parameters()):
+        assert rel_l2(a, b) < 1e-5, k
