@@ -442,9 +442,10 @@ def partitioned_cfg4(device, rank, world, iters=5):
 def cfg5_block(device, rank, world, dist_on, n_cases=10000, nodes=20000, per_launch=16, distinct=48):
     """Every rank takes ``case_ids[rank::world]`` (inference_gnn.py:380-398 loops the cases independently).  Per launch
     ``per_launch`` packed cases (pos, normal, faces, globals - the content of the reference's three case files) go from
-    pinned host memory to the device, the graph is built there (``dfw_faces_to_csr`` + ``dfw_node_features``), one forward
-    (H = 128, L = 4, fp32) runs and the per-case mean prediction comes back to the host.  ``distinct`` different synthetic
-    cases per rank are cycled (generating 10k on the host would take minutes); everything else is per case."""
+    pinned host memory to the device, the graph is built there (``dfw_faces_to_csr`` + ``dfw_node_features_batched``), one
+    forward (H = 128, L = 4) runs and the per-case mean prediction comes back to the host.  ``distinct`` different synthetic
+    cases per rank are cycled (generating 10k on the host would take minutes); everything else is per case.
+    fp32 is the headline (`value`); the same loop with bf16 activations is reported beside it."""
     import torch.distributed as dist
 
     from deep_fem_uav_wing.gnn import ops
@@ -456,76 +457,84 @@ def cfg5_block(device, rank, world, dist_on, n_cases=10000, nodes=20000, per_lau
     for i in range(min(distinct, mine)):
         m = synth.surface_tri_wing(nodes, seed=1000 + rank * distinct + i)
         p = m["params"]
+        gp = [(p["span_m"] - 1.0) / 1.0, (p["chord_m"] - 0.2) / 0.3, p["sweep_deg"] / 30.0, (p["thickness_ratio"] - 0.05) / 0.10]  # dataset.py:122-127
         cases.append({"pos": torch.from_numpy(m["pos"]).pin_memory(), "normal": torch.from_numpy(m["normal"]).pin_memory(),
                       "faces": torch.from_numpy(m["faces"].astype(np.int64)).pin_memory(), "n": m["num_nodes"],
-                      "gp": [p["span_m"], p["chord_m"], p["sweep_deg"], p["thickness_ratio"]]})
-    torch.manual_seed(42)
-    model = GraphSAGEModel(10, HIDDEN, 1, LAYERS).to(device).eval()
+                      "gp": torch.tensor(gp, dtype=torch.float32).pin_memory()})
     res_pin = torch.empty(per_launch, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=device)
-    h2d = 0
+    n_launch = (mine + per_launch - 1) // per_launch
+    groups = [[cases[(l * per_launch + j) % len(cases)] for j in range(min(per_launch, mine - l * per_launch))] for l in range(n_launch)]
+    counters = {"h2d": 0}
 
     def stage(group):
-        nonlocal h2d
         with torch.cuda.stream(copy_stream):
             dev = []
             for c in group:
                 dev.append((c["pos"].to(device, non_blocking=True), c["normal"].to(device, non_blocking=True),
-                            c["faces"].to(device, non_blocking=True), c["n"], c["gp"]))
-                h2d += c["pos"].numel() * 4 + c["normal"].numel() * 4 + c["faces"].numel() * 8
+                            c["faces"].to(device, non_blocking=True), c["n"], c["gp"].to(device, non_blocking=True)))
+                counters["h2d"] += c["pos"].numel() * 4 + c["normal"].numel() * 4 + c["faces"].numel() * 8 + 16
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return dev, ev
 
-    def run(dev):
-        xs, fs, off, ptr = [], [], 0, [0]
-        for pos, nrm, faces, n, gp in dev:
-            x, _ = ops.node_features(pos, nrm, None, gp)  # per-mesh min-max normalisation (dataset.py:130-136)
-            xs.append(x)
+    def run(model, dev):
+        fs, off, ptr = [], 0, [0]
+        for _, _, faces, n, _ in dev:
             fs.append(faces + off)
             off += n
             ptr.append(off)
-        # ONE graph build for the launch: the faces of the disjoint union (one 8-byte edge-count read per launch)
+        # ONE feature launch pair (per-case min-max normalisation, dataset.py:130-136) and ONE graph build for the whole launch:
+        # the faces of the disjoint union (one 8-byte edge-count read per launch)
+        x, _ = ops.node_features_batched(torch.cat([d[0] for d in dev]), torch.cat([d[1] for d in dev]), None, torch.stack([d[4] for d in dev]),
+                                         torch.tensor(ptr, dtype=torch.int64, device=device), max(d[3] for d in dev))
         g, ei = ops.faces_to_graph(torch.cat(fs), off)
         with torch.no_grad():
-            out = model(torch.cat(xs), ei)
+            out = model(x, ei)
         if all(ptr[i + 1] - ptr[i] == ptr[1] for i in range(len(dev))):
-            means = out.view(len(dev), -1).mean(dim=1)
+            means = out.float().view(len(dev), -1).mean(dim=1)
         else:
-            means = torch.stack([out[ptr[i]:ptr[i + 1]].mean() for i in range(len(dev))])
+            means = torch.stack([out[ptr[i]:ptr[i + 1]].float().mean() for i in range(len(dev))])
         res_pin[: len(dev)].copy_(means, non_blocking=True)
         ops.clear_graph_cache()
 
-    n_launch = (mine + per_launch - 1) // per_launch
-    groups = [[cases[(l * per_launch + j) % len(cases)] for j in range(min(per_launch, mine - l * per_launch))] for l in range(n_launch)]
-    for l in range(2):  # warm-up
-        dev, ev = stage(groups[l % n_launch])
-        torch.cuda.current_stream(device).wait_event(ev)
-        run(dev)
-    torch.cuda.synchronize(device)
-    h2d = 0
-    k0 = ops.LAUNCH_COUNTER["kernels"]
-    if dist_on:
-        dist.barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    nxt = stage(groups[0])
-    for l in range(n_launch):
-        dev, ev = nxt
-        if l + 1 < n_launch:
-            nxt = stage(groups[l + 1])  # H2D of the next launch overlaps this launch's graph build + forward
-        torch.cuda.current_stream(device).wait_event(ev)
-        run(dev)
-    b.record()
-    torch.cuda.synchronize(device)
-    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
-    if dist_on:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return {"value": n_cases / (ms.item() * 1e-3), "unit": "meshes/s", "n_cases": n_cases, "cases_per_rank": mine, "nodes_per_case": nodes,
-            "nodes_per_sec": n_cases * nodes / (ms.item() * 1e-3), "ms_total": ms.item(), "cases_per_launch": per_launch, "hidden": HIDDEN,
+    def measure(dtype):
+        torch.manual_seed(42)
+        model = GraphSAGEModel(10, HIDDEN, 1, LAYERS).to(device).eval().set_compute_dtype(dtype)
+        for l in range(2):  # warm-up
+            dev, ev = stage(groups[l % n_launch])
+            torch.cuda.current_stream(device).wait_event(ev)
+            run(model, dev)
+        torch.cuda.synchronize(device)
+        counters["h2d"] = 0
+        k0 = ops.LAUNCH_COUNTER["kernels"]
+        if dist_on:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nxt = stage(groups[0])
+        for l in range(n_launch):
+            dev, ev = nxt
+            if l + 1 < n_launch:
+                nxt = stage(groups[l + 1])  # H2D of the next launch overlaps this launch's graph build + forward
+            torch.cuda.current_stream(device).wait_event(ev)
+            run(model, dev)
+        b.record()
+        torch.cuda.synchronize(device)
+        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+        if dist_on:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), ops.LAUNCH_COUNTER["kernels"] - k0
+
+    ms32, launches = measure(torch.float32)
+    h2d = counters["h2d"]
+    ms16, _ = measure(torch.bfloat16)
+    return {"value": n_cases / (ms32 * 1e-3), "unit": "meshes/s", "n_cases": n_cases, "cases_per_rank": mine, "nodes_per_case": nodes,
+            "nodes_per_sec": n_cases * nodes / (ms32 * 1e-3), "ms_total": ms32, "cases_per_launch": per_launch, "hidden": HIDDEN,
             "layers": LAYERS, "dtype": "f32", "h2d_bytes_per_case": h2d // max(mine, 1), "d2h_bytes_per_case": 4,
-            "gpu_launches": ops.LAUNCH_COUNTER["kernels"] - k0, "sharding": "case_ids[rank::world], no communication",
-            "path": "packed case (pos, normal, faces) in pinned host memory -> H2D -> dfw_node_features + dfw_faces_to_csr -> "
+            "gpu_launches": launches, "sharding": "case_ids[rank::world], no communication",
+            "bf16": {"value": n_cases / (ms16 * 1e-3), "unit": "meshes/s", "ms_total": ms16, "what": "same loop, bf16 activations (fp32 first layer, fp32 accumulation)"},
+            "path": "packed case (pos, normal, faces) in pinned host memory -> H2D -> dfw_node_features_batched + dfw_faces_to_csr -> "
                     "GraphSAGEModel forward -> per-case mean prediction D2H", "data": f"{len(cases)} distinct synthetic cases per rank, cycled"}
 
 

@@ -113,8 +113,116 @@ __global__ void __launch_bounds__(kFeatThreads) k_node_features(const FeatArgs p
     }
 }
 
+// ---- batched form: B cases concatenated (rows case_ptr[b] .. case_ptr[b+1]), per-case min/max and global parameters ----
+// One launch pair for a whole inference launch of the design-screening loop (inference_gnn.py:380-398 builds one case at a
+// time): the per-case kernels are tiny (20k nodes) and their 2 x B launches were host overhead, not GPU work.
+__global__ void __launch_bounds__(kFeatThreads) k_pos_minmax_cases(const float* __restrict__ pos, const int64_t* __restrict__ case_ptr,
+                                                                   float* __restrict__ mm /*[B][8]*/) {
+    __shared__ float sh[kFeatThreads / 32][6];
+    const int64_t r0 = case_ptr[blockIdx.x], r1 = case_ptr[blockIdx.x + 1];
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = pos[3 * i + a];
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { sh[wid][a] = lo[a]; sh[wid][3 + a] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        float v = sh[0][k];
+        for (int w = 1; w < kFeatThreads / 32; ++w) v = k < 3 ? fminf(v, sh[w][k]) : fmaxf(v, sh[w][k]);
+        mm[8 * (int64_t)blockIdx.x + k] = v;
+    }
+}
+
+struct FeatCasesArgs {
+    const float* pos; const float* normal; const float* stress; const float* mm; const float* gp; const int64_t* case_ptr;
+    int normalize_pos, log_scale;
+    float* x; float* y;
+};
+
+__global__ void __launch_bounds__(kFeatThreads) k_node_features_cases(const FeatCasesArgs p) {
+    const int b = blockIdx.y;
+    const int64_t r0 = p.case_ptr[b], r1 = p.case_ptr[b + 1];
+    float mn[3] = {0.f, 0.f, 0.f}, rg[3] = {1.f, 1.f, 1.f};
+    if (p.normalize_pos) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = p.mm[8 * b + a];
+            rg[a] = __fsub_rn(p.mm[8 * b + 3 + a], p.mm[8 * b + a]);
+            if (rg[a] < 1e-8f) rg[a] = 1.0f;  // dataset.py:135
+        }
+    }
+    const float g0 = p.gp[4 * b], g1 = p.gp[4 * b + 1], g2 = p.gp[4 * b + 2], g3 = p.gp[4 * b + 3];
+    for (int64_t i = r0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < r1; i += (int64_t)gridDim.x * blockDim.x) {
+        float* xo = p.x + 10 * i;
+        const float px = p.pos[3 * i], py = p.pos[3 * i + 1], pz = p.pos[3 * i + 2];
+        if (p.normalize_pos) {
+            xo[0] = __fdiv_rn(__fsub_rn(px, mn[0]), rg[0]);
+            xo[1] = __fdiv_rn(__fsub_rn(py, mn[1]), rg[1]);
+            xo[2] = __fdiv_rn(__fsub_rn(pz, mn[2]), rg[2]);
+        } else {
+            xo[0] = px; xo[1] = py; xo[2] = pz;
+        }
+        const float nx = p.normal[3 * i], ny = p.normal[3 * i + 1], nz = p.normal[3 * i + 2];
+        float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+        if (len < 1e-8f) len = 1.0f;  // dataset.py:140
+        xo[3] = __fdiv_rn(nx, len);
+        xo[4] = __fdiv_rn(ny, len);
+        xo[5] = __fdiv_rn(nz, len);
+        xo[6] = g0; xo[7] = g1; xo[8] = g2; xo[9] = g3;
+        if (p.y) {
+            const float s = p.stress[i];
+            p.y[i] = p.log_scale ? log1pf(s) : s;  // dataset.py:148-151
+        }
+    }
+}
+
 }  // namespace
 }  // namespace dfw
+
+extern "C" size_t dfw_node_features_batched_ws_bytes(int64_t B) { return B > 0 ? (size_t)B * 8 * sizeof(float) : 0; }
+
+extern "C" int dfw_node_features_batched(const float* pos, const float* normal, const float* stress, const float* global_params /*device [B,4]*/,
+                                         const int64_t* case_ptr /*device [B+1]*/, int64_t B, int64_t max_case_rows, int normalize_pos, int log_scale,
+                                         float* x, float* y, void* ws, size_t ws_bytes, dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(B >= 0 && max_case_rows >= 0, "dfw_node_features_batched: negative size");
+    if (B == 0 || max_case_rows == 0) return 0;
+    DFW_REQUIRE(B <= 65535, "dfw_node_features_batched: at most 65535 cases per call");
+    DFW_REQUIRE(pos && normal && x && global_params && case_ptr, "dfw_node_features_batched: null pointer");
+    DFW_REQUIRE((y == nullptr) || stress, "dfw_node_features_batched: y requested without stress");
+    DFW_REQUIRE(ws && ws_bytes >= dfw_node_features_batched_ws_bytes(B), "dfw_node_features_batched: workspace too small");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    float* mm = static_cast<float*>(ws);
+    if (normalize_pos) {
+        k_pos_minmax_cases<<<(unsigned)B, kFeatThreads, 0, s>>>(pos, case_ptr, mm);
+        DFW_LAUNCH_CHECK();
+    }
+    FeatCasesArgs a{};
+    a.pos = pos; a.normal = normal; a.stress = stress; a.mm = mm; a.gp = global_params; a.case_ptr = case_ptr;
+    a.normalize_pos = normalize_pos; a.log_scale = log_scale; a.x = x; a.y = y;
+    const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((max_case_rows + kFeatThreads - 1) / kFeatThreads, 64));
+    k_node_features_cases<<<dim3(bx, (unsigned)B, 1), kFeatThreads, 0, s>>>(a);
+    DFW_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" size_t dfw_node_features_ws_bytes(int64_t N) {
     (void)N;

@@ -261,6 +261,28 @@ def node_features(pos: torch.Tensor, normal: torch.Tensor, stress: torch.Tensor 
     return x, y
 
 
+def node_features_batched(pos, normal, stress, global_params, case_ptr, max_case_rows: int, normalize_pos=True, log_scale=True):
+    """``dfw_node_features_batched``: features of B concatenated cases in one launch pair.  ``global_params`` fp32 [B,4] (scaled,
+    ``dataset.py:122-127``) and ``case_ptr`` int64 [B+1] are DEVICE tensors; per-case min-max normalisation of ``pos``."""
+    _require_cuda(pos, "pos")
+    pos = pos.to(torch.float32).contiguous()
+    normal = normal.to(torch.float32).contiguous()
+    N, dev, B = int(pos.shape[0]), pos.device, int(case_ptr.numel()) - 1
+    x = torch.empty(N, 10, dtype=torch.float32, device=dev)
+    y = None
+    if stress is not None:
+        stress = stress.to(torch.float32).contiguous()
+        y = torch.empty(N, 1, dtype=torch.float32, device=dev)
+    ws_bytes = lib.dfw_node_features_batched_ws_bytes(B)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+    gp = global_params.to(device=dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev), _prof("node_features", 72 * N):
+        check(lib.dfw_node_features_batched(pos.data_ptr(), normal.data_ptr(), _ptr(stress), gp.data_ptr(), case_ptr.data_ptr(), B, int(max_case_rows),
+                                            int(bool(normalize_pos)), int(bool(log_scale)), x.data_ptr(), _ptr(y), ws.data_ptr(), ws.numel(), _stream(pos)))
+    LAUNCH_COUNTER["kernels"] += 2
+    return x, y
+
+
 _CSR_CACHE: "OrderedDict[tuple, CSRGraph]" = OrderedDict()
 _CSR_CACHE_SIZE = 16  # loaders create a new edge_index tensor per step: a long LRU only pins dead batches' CSRs in HBM
 

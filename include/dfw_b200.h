@@ -99,6 +99,13 @@ size_t dfw_node_features_ws_bytes(int64_t N);
 int dfw_node_features(const float* pos, const float* normal, const float* stress, const float* global_params4,
                       int normalize_pos, int log_scale, float* x, float* y, int64_t N, void* ws, size_t ws_bytes,
                       dfw_stream_t stream);
+/*     Batched form for the design-screening loop (inference_gnn.py:380-398 handles one case at a time): B cases concatenated,
+ *     rows case_ptr[b] .. case_ptr[b+1] (device int64 [B+1]), global_params device fp32 [B,4] (already scaled, dataset.py:122-127),
+ *     per-case min-max normalisation.  Bit-identical to B calls of dfw_node_features.  max_case_rows sizes the grid. */
+size_t dfw_node_features_batched_ws_bytes(int64_t B);
+int dfw_node_features_batched(const float* pos, const float* normal, const float* stress, const float* global_params,
+                              const int64_t* case_ptr, int64_t B, int64_t max_case_rows, int normalize_pos, int log_scale,
+                              float* x, float* y, void* ws, size_t ws_bytes, dfw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (b) deterministic segmented neighbour aggregation (no atomics):

@@ -466,3 +466,24 @@ def test_faces_to_graph_on_a_config_sized_surface_mesh(ops):
     a = ops.aggregate(g.rowptr, g.col, g.inv_deg, x)
     g_host = ops.get_graph(torch.from_numpy(m["edge_index"]).cuda(), n)
     assert torch.equal(a, ops.aggregate(g_host.rowptr, g_host.col, g_host.inv_deg, x))
+
+
+def test_node_features_batched_equals_per_case_calls(ops):
+    """dfw_node_features_batched (B concatenated cases, per-case min-max) is bit-identical to B calls of dfw_node_features."""
+    from deep_fem_uav_wing.gnn import synth
+
+    meshes = [synth.surface_tri_wing(900 + 130 * i, seed=20 + i) for i in range(5)]
+    gps = [[0.1 * i, 0.2, 0.3 + 0.05 * i, 0.4] for i in range(5)]
+    xs, ys = [], []
+    for m, gp in zip(meshes, gps):
+        x, y = ops.node_features(torch.from_numpy(m["pos"]).cuda(), torch.from_numpy(m["normal"]).cuda(), torch.from_numpy(m["stress_vm_raw"]).cuda(), gp)
+        xs.append(x)
+        ys.append(y)
+    ptr = np.concatenate([[0], np.cumsum([m["num_nodes"] for m in meshes])])
+    xb, yb = ops.node_features_batched(torch.cat([torch.from_numpy(m["pos"]) for m in meshes]).cuda(), torch.cat([torch.from_numpy(m["normal"]) for m in meshes]).cuda(),
+                                       torch.cat([torch.from_numpy(m["stress_vm_raw"]) for m in meshes]).cuda(), torch.tensor(gps, dtype=torch.float32).cuda(),
+                                       torch.from_numpy(ptr).cuda(), max(m["num_nodes"] for m in meshes))
+    assert torch.equal(xb, torch.cat(xs)) and torch.equal(yb, torch.cat(ys))
+    xn, yn = ops.node_features_batched(torch.cat([torch.from_numpy(m["pos"]) for m in meshes]).cuda(), torch.cat([torch.from_numpy(m["normal"]) for m in meshes]).cuda(), None,
+                                       torch.tensor(gps, dtype=torch.float32).cuda(), torch.from_numpy(ptr).cuda(), 2000, normalize_pos=False)
+    assert yn is None and torch.equal(xn[:, 3:], xb[:, 3:]) and torch.equal(xn[:, :3], torch.cat([torch.from_numpy(m["pos"]) for m in meshes]).cuda())
