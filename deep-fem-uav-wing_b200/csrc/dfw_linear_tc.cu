@@ -756,6 +756,230 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* cvec, 
     if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
 }
 
+// Lean form of epilogue_tile for k_linear_tcp (same arithmetic, same staging layout).  tools/lin_knock.py + the ncu source page
+// showed the epilogue warps, not the main loop, pacing the persistent kernel (epilogue alone 114 us of the 134 us SAGE forward;
+// main loop alone 77 us): ~6.4k warp instructions per tile and warp at ~0.2 IPC, a third of them address / predicate / branch
+// overhead of the write-back (64-bit row bound checks and a reconvergence region per store, register copies of the prefetched
+// residual, special registers re-read per round), and a quarter of the stall samples on the residual loads, requested one
+// 64-byte round (~200 clk) ahead.  Here: FULL tiles carry no row predicates, every address is a per-tile lane pointer plus
+// compile-time multiples of one step, the residual of a whole 32-column group is requested BEFORE the group's TMEM load and
+// math (no copies: each round owns its registers), and main + cross accumulators are loaded with one wait.
+template <typename T, bool TF32, bool FULL>
+__device__ __forceinline__ void epilogue_tile2(const Args& p, const float* cvec, int HP, uint8_t* slice, uint32_t t_row, int64_t m_base, int q, int lane) {
+    constexpr int SCOLS = 64 / (int)sizeof(T);  // columns per 64-byte staging round: 16 fp32 / 32 bf16
+    constexpr int ROUNDS = 32 / SCOLS;          // rounds per 32-column group
+    constexpr int EPS = 16 / (int)sizeof(T);    // elements per 16-byte slot
+    const int H = p.Hout;
+    const int n32 = H / 32;
+    const bool ln = p.flags & DFW_EP_LAYERNORM, relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
+    const float4* bias4 = reinterpret_cast<const float4*>(cvec);
+    const float4* gam4 = reinterpret_cast<const float4*>(cvec + HP);
+    const float4* bet4 = reinterpret_cast<const float4*>(cvec + 2 * HP);
+    const float4* rdw4 = reinterpret_cast<const float4*>(cvec + 3 * HP);
+    const uint32_t row_bytes = (uint32_t)H * (uint32_t)sizeof(T);
+    const bool y_in_tmem = ln || p.pre_out;
+    // thread-per-row domain (TMEM lane = tile row)
+    const int64_t row = m_base + q * 32 + lane;
+    const bool rok = FULL || row < p.N;
+    const bool has_rs = p.row_scale != nullptr;
+    const float rs = (has_rs && rok) ? __ldg(p.row_scale + row) : 1.f;
+    const uint32_t row_key = drop ? dropout_row_key(resolve_seed(p.seed, p.flags), (uint64_t)row) : 0u;
+    // write-back domain: 4 lanes = one 64-byte row piece; iteration `it` handles warp row it*8 + (lane >> 2)
+    const int jj = lane & 3, rr0 = lane >> 2;
+    const int64_t wrow = m_base + q * 32 + rr0;
+    const int nvalid = FULL ? 32 : (int)min((int64_t)32, max((int64_t)0, p.N - wrow));  // iteration `it` is in range iff it*8 < nvalid
+    const size_t lane_off = (size_t)wrow * row_bytes + (size_t)jj * 16;
+    const size_t step = (size_t)8 * row_bytes;
+    uint8_t* const sts_row = slice + lane * 64;
+    const int sts_sw = (lane >> 1) & 3;
+    const uint8_t* const lds_ptr = slice + rr0 * 64 + ((jj ^ ((lane >> 3) & 3)) << 4);  // + it * 512 (the swizzle term does not depend on `it`)
+    uint8_t* const out_lane = p.out ? static_cast<uint8_t*>(p.out) + lane_off : nullptr;
+    uint8_t* const pre_lane = p.pre_out ? static_cast<uint8_t*>(p.pre_out) + lane_off : nullptr;
+    const uint8_t* const res_lane = p.residual ? static_cast<const uint8_t*>(p.residual) + lane_off : nullptr;
+    const bool has_res = res_lane != nullptr;
+
+    auto load_res = [&](const uint8_t* src, uint4 (&dst)[4]) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            if (FULL || it * 8 < nvalid) dst[it] = *reinterpret_cast<const uint4*>(src + it * step);
+            else dst[it] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    // 64 bytes of this thread's row (pk) -> staging -> coalesced global store, + residual piece (rv) if given
+    auto stage_and_store = [&](uint8_t* dst, const uint4 (&pk)[4], const uint4* rv) {
+        __syncwarp();  // the previous round's read-back is done
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(sts_row + ((j ^ sts_sw) << 4)) = pk[j];
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            uint4 v = *reinterpret_cast<const uint4*>(lds_ptr + it * 512);
+            if (rv) {
+                const uint4 r4 = rv[it];
+                if constexpr (sizeof(T) == 4) {
+                    v.x = __float_as_uint(__uint_as_float(v.x) + __uint_as_float(r4.x));
+                    v.y = __float_as_uint(__uint_as_float(v.y) + __uint_as_float(r4.y));
+                    v.z = __float_as_uint(__uint_as_float(v.z) + __uint_as_float(r4.z));
+                    v.w = __float_as_uint(__uint_as_float(v.w) + __uint_as_float(r4.w));
+                } else {
+                    Vec16<T> a, b;
+                    a.v = v;
+                    b.v = r4;
+                    float fa[8], fb[8];
+                    a.to_float(fa);
+                    b.to_float(fb);
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8) fa[e8] += fb[e8];
+                    a.from_float(fa);
+                    v = a.v;
+                }
+            }
+            if (FULL || it * 8 < nvalid) *reinterpret_cast<uint4*>(dst + it * step) = v;
+        }
+    };
+    auto pack = [&](const float* src, uint4 (&pk)[4]) {  // SCOLS values -> 64 bytes
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if constexpr (sizeof(T) == 4) {
+                pk[j] = make_uint4(__float_as_uint(src[4 * j]), __float_as_uint(src[4 * j + 1]), __float_as_uint(src[4 * j + 2]), __float_as_uint(src[4 * j + 3]));
+            } else {
+                Vec16<T> u;
+                u.from_float(src + EPS * j);
+                pk[j] = u.v;
+            }
+        }
+    };
+    auto load_acc = [&](int c0, float* v) {  // hi*hi + cross terms, summed in round-to-nearest fp32 (see tmem_combine)
+        if (TF32 && p.nacc != 0) {
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(t_row + c0, ra);
+            tmem_ld32_issue(t_row + p.Npad + c0, rb);
+            tmem_ld_wait(ra);
+            tmem_ld_wait(rb);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+        } else {
+            tmem_ld32(t_row + c0, v);
+        }
+    };
+    // y = (acc + bias) * row_scale for the 32 columns starting at c0
+    auto finish_y = [&](int c0, float* v) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float4 b = bias4[c0 / 4 + g];
+            v[4 * g] += b.x;
+            v[4 * g + 1] += b.y;
+            v[4 * g + 2] += b.z;
+            v[4 * g + 3] += b.w;
+        }
+        if (has_rs) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= rs;
+        }
+    };
+    float mean = 0.f, rstd = 1.f;
+    // ---- pass 1: y written back to region 0, row sum, pre-activation tensor ----
+    if (y_in_tmem) {
+        float s = 0.f;
+        for (int g = 0; g < n32; ++g) {
+            const int c0 = g * 32;
+            float v[32];
+            load_acc(c0, v);
+            finish_y(c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += v[j];
+            tmem_st32_nowait(t_row + c0, v);
+            if (pre_lane) {
+#pragma unroll
+                for (int h = 0; h < ROUNDS; ++h) {
+                    uint4 pk[4];
+                    pack(v + h * SCOLS, pk);
+                    stage_and_store(pre_lane + (size_t)(c0 + h * SCOLS) * sizeof(T), pk, nullptr);
+                }
+            }
+        }
+        tmem_st_wait();
+        mean = s / (float)H;
+    }
+    // ---- pass 2: variance around the mean (two-pass, like torch) ----
+    if (ln) {
+        float qs = 0.f;
+        for (int g = 0; g < n32; ++g) {
+            float v[32];
+            tmem_ld32(t_row + g * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float d = v[j] - mean;
+                qs = fmaf(d, d, qs);
+            }
+        }
+        rstd = rsqrtf(qs / (float)H + p.eps);
+        if (p.ln_stats && rok) {
+            p.ln_stats[2 * row] = mean;
+            p.ln_stats[2 * row + 1] = rstd;
+        }
+    }
+    // ---- pass 3: normalise, ReLU, dropout, row-dot, (+ residual in the write-back), store ----
+    float dot = 0.f;
+    for (int g = 0; g < n32; ++g) {
+        const int c0 = g * 32;
+        uint4 rv[ROUNDS][4];
+        if (has_res) {
+#pragma unroll
+            for (int h = 0; h < ROUNDS; ++h) load_res(res_lane + (size_t)(c0 + h * SCOLS) * sizeof(T), rv[h]);
+        }
+        float v[32];
+        if (y_in_tmem) {
+            tmem_ld32(t_row + c0, v);
+        } else {
+            load_acc(c0, v);
+            finish_y(c0, v);
+        }
+        if (ln) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const float4 ga = gam4[c0 / 4 + g4], be = bet4[c0 / 4 + g4];
+                v[4 * g4] = (v[4 * g4] - mean) * rstd * ga.x + be.x;
+                v[4 * g4 + 1] = (v[4 * g4 + 1] - mean) * rstd * ga.y + be.y;
+                v[4 * g4 + 2] = (v[4 * g4 + 2] - mean) * rstd * ga.z + be.z;
+                v[4 * g4 + 3] = (v[4 * g4 + 3] - mean) * rstd * ga.w + be.w;
+            }
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (drop) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t bits = dropout_bits(row_key, (uint32_t)(c0 + j));
+                v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
+            }
+        }
+        if (p.rowdot_out) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const float4 w = rdw4[c0 / 4 + g4];
+                dot = fmaf(v[4 * g4], w.x, dot);
+                dot = fmaf(v[4 * g4 + 1], w.y, dot);
+                dot = fmaf(v[4 * g4 + 2], w.z, dot);
+                dot = fmaf(v[4 * g4 + 3], w.w, dot);
+            }
+        }
+        if (out_lane) {
+#pragma unroll
+            for (int h = 0; h < ROUNDS; ++h) {
+                uint4 pk[4];
+                pack(v + h * SCOLS, pk);
+                uint8_t* dst = out_lane + (size_t)(c0 + h * SCOLS) * sizeof(T);
+                if (has_res) stage_and_store(dst, pk, rv[h]);
+                else stage_and_store(dst, pk, nullptr);
+            }
+        }
+    }
+    if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
+}
+
 // =====================================================================================================================
 // Persistent variant: one CTA per SM loops over 128-row tiles.
 //   * K chunks of 128 bytes (SWIZZLE_128B) for fp32 too: the TMA unit retires ~one box ROW per 2 clk whatever its width
@@ -852,7 +1076,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
       if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t stage_tx = (uint32_t)(kTileM * 128 + p.Npad * 128 * (TF32 ? 2 : 1));
+            const bool ld_a = !(p.knock & 16), ld_w = !(p.knock & 4);
+            const uint32_t stage_tx = (uint32_t)((ld_a ? kTileM * 128 : 0) + (ld_w ? p.Npad * 128 * (TF32 ? 2 : 1) : 0));
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < nmine; ++i) {
@@ -862,10 +1087,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
                     const int kc = (seg ? c - p.chunks[0] : c) * KPC;
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* st = smem + (size_t)stage * L.stage_bytes;
-                    mbar_arrive_expect_tx(&full[stage], stage_tx);
-                    tma_load_2d(st + L.a_hi, &maps.a[seg], &full[stage], kc, m_base);
-                    tma_load_2d(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0);
-                    if (TF32) tma_load_2d(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0);
+                    if (stage_tx) mbar_arrive_expect_tx(&full[stage], stage_tx);
+                    else mbar_arrive(&full[stage]);
+                    if (ld_a) tma_load_2d(st + L.a_hi, &maps.a[seg], &full[stage], kc, m_base);
+                    if (ld_w) tma_load_2d(st + L.w_hi, &maps.w_hi[seg], &full[stage], kc, 0);
+                    if (TF32 && ld_w) tma_load_2d(st + L.w_lo, &maps.w_lo[seg], &full[stage], kc, 0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -891,6 +1117,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
                     const uint32_t st = smem_u32(smem + (size_t)stage * L.stage_bytes);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // UMMA_K = 32 bytes
+                        if (p.knock & 2) break;
                         const uint64_t a_hi = dbase + ((st + L.a_hi + k * 32) >> 4);
                         const uint64_t w_hi = dbase + ((st + L.w_hi + k * 32) >> 4);
                         if (TF32) {
@@ -929,8 +1156,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
                 uint8_t* st = smem + (size_t)stage * L.stage_bytes;
                 const float4* hi = reinterpret_cast<const float4*>(st + L.a_hi);
                 float4* lo = reinterpret_cast<float4*>(st + L.a_lo);
+                if (!(p.knock & 1)) {
 #pragma unroll
-                for (int j = 0; j < (kTileM * 128 / 16) / 128; ++j) lo[ct + j * 128] = tf32_lo(hi[ct + j * 128]);
+                    for (int j = 0; j < (kTileM * 128 / 16) / 128; ++j) lo[ct + j * 128] = tf32_lo(hi[ct + j * 128]);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&conv[stage]);
@@ -951,7 +1180,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
             fence_tc_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * buf_cols;
 
-            epilogue_tile<T, TF32>(p, cvec, HP, slice, t_row, m_base, q, lane);
+            if (!(p.knock & 8)) {
+                if (m_base + kTileM <= p.N) epilogue_tile2<T, TF32, true>(p, cvec, HP, slice, t_row, m_base, q, lane);
+                else epilogue_tile2<T, TF32, false>(p, cvec, HP, slice, t_row, m_base, q, lane);
+            }
             fence_tc_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[ab]);
@@ -1449,6 +1681,8 @@ int linear_tc_launch(const void* a1, const void* w1, int64_t k1, const void* a2,
             args.Npad = Npad;
             static const int env_merge = [] { const char* e = getenv("DFW_TC_MERGE"); return e ? atoi(e) : 0; }();  // dev probe
             args.nacc = env_merge ? 0 : 1;
+            static const int env_knock = [] { const char* e = getenv("DFW_TC_KNOCK"); return e ? atoi(e) : 0; }();  // dev probe: see Args::knock
+            args.knock = env_knock;
             int cols = 32;
             while (cols < 2 * regions * Npad) cols <<= 1;
             args.tmem_cols = cols;

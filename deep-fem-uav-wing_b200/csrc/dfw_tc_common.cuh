@@ -20,6 +20,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait carries a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+// polling every ~50 ns - the plain loop of the waiting warps took a third of the persistent linear's issue slots, which its
+// epilogue needs (ncu r02: 4.3 M polls x ~5 instructions against 40 M epilogue instructions per launch).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok;
@@ -28,11 +31,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(20000u)
             : "memory");
         if (!ok && ++spins > (1u << 24)) {  // a legitimate wait lasts microseconds: this is a protocol bug, fail loudly
             printf("dfw_linear_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
