@@ -548,224 +548,17 @@ __global__ void __launch_bounds__(kThreads) k_linear_tc(const __grid_constant__ 
 // The three epilogue passes of one 128-row tile for ONE thread (= tile row `q*32 + lane`, whose accumulator lives in TMEM lane
 // `q*32 + lane` from column `t_row`): y = (acc + bias) * row_scale, LayerNorm, ReLU, dropout, row-dot, residual, stores through the
 // warp's private staging slice.  Shared by the persistent kernels (k_linear_tcp, k_linear_tc2).
-template <typename T, bool TF32>
-__device__ __forceinline__ void epilogue_tile(const Args& p, const float* cvec, int HP, uint8_t* slice, uint32_t t_row, int64_t m_base, int q, int lane) {
-    constexpr int SCOLS = 64 / (int)sizeof(T);  // columns per 64-byte staging round: 16 fp32 / 32 bf16
-    const int r_in_tile = q * 32 + lane;
-    const int H = p.Hout;
-    const int n32 = H / 32;
-    const bool ln = p.flags & DFW_EP_LAYERNORM, relu = p.flags & DFW_EP_RELU, drop = p.flags & DFW_EP_DROPOUT;
-    const float4* bias4 = reinterpret_cast<const float4*>(cvec);
-    const float4* gam4 = reinterpret_cast<const float4*>(cvec + HP);
-    const float4* bet4 = reinterpret_cast<const float4*>(cvec + 2 * HP);
-    const float4* rdw4 = reinterpret_cast<const float4*>(cvec + 3 * HP);
-    const uint32_t row_bytes = (uint32_t)H * (uint32_t)sizeof(T);
-    const bool y_in_tmem = ln || p.pre_out;
-    const int64_t row = m_base + r_in_tile;
-    const bool rok = row < p.N;
-    const float rs = (p.row_scale && rok) ? __ldg(p.row_scale + row) : 1.f;
-    const uint32_t row_key = drop ? dropout_row_key(resolve_seed(p.seed, p.flags), (uint64_t)row) : 0u;
-
-    // one 64-byte piece per row of this warp's 32 rows -> global, coalesced (4 lanes = one row piece), + residual.
-    // The residual pieces of the NEXT 64-byte round are requested before this round is staged, so their latency runs under the
-    // staging, the stores and the next group's TMEM load + math (loaded on demand they cost ~1 us per round: 8 us per fp32 tile).
-    uint4 rpre[4];
-    int rpre_col = -1;
-    auto load_res = [&](const void* rbase, int col0, uint4 (&dst)[4]) {
-        const size_t coff = (size_t)col0 * sizeof(T) + (size_t)(lane & 3) * 16;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int64_t grow = m_base + q * 32 + it * 8 + (lane >> 2);
-            dst[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (grow < p.N) dst[it] = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(rbase) + (size_t)grow * row_bytes + coff);
-        }
-    };
-    auto write_out = [&](void* gbase, const void* rbase, int col0, const uint4 (&pk)[4]) {
-        uint4 rv[4];
-        if (rbase) {
-            if (rpre_col == col0) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) rv[it] = rpre[it];
-            } else {
-                load_res(rbase, col0, rv);
-            }
-            if (col0 + SCOLS < H) {
-                load_res(rbase, col0 + SCOLS, rpre);
-                rpre_col = col0 + SCOLS;
-            }
-        }
-        __syncwarp();  // the previous round's read-back is done
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slice + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk[j];
-        __syncwarp();
-        const int jj = lane & 3;
-        const size_t coff = (size_t)col0 * sizeof(T) + (size_t)jj * 16;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + (lane >> 2);
-            uint4 v = *reinterpret_cast<const uint4*>(slice + rr * 64 + ((jj ^ ((rr >> 1) & 3)) << 4));
-            const int64_t grow = m_base + q * 32 + rr;
-            if (grow < p.N) {
-                const size_t off = (size_t)grow * row_bytes + coff;
-                if (rbase) {
-                    const uint4 r4 = rv[it];
-                    if constexpr (sizeof(T) == 4) {
-                        v.x = __float_as_uint(__uint_as_float(v.x) + __uint_as_float(r4.x));
-                        v.y = __float_as_uint(__uint_as_float(v.y) + __uint_as_float(r4.y));
-                        v.z = __float_as_uint(__uint_as_float(v.z) + __uint_as_float(r4.z));
-                        v.w = __float_as_uint(__uint_as_float(v.w) + __uint_as_float(r4.w));
-                    } else {
-                        Vec16<T> a, b;
-                        a.v = v;
-                        b.v = r4;
-                        float fa[8], fb[8];
-                        a.to_float(fa);
-                        b.to_float(fb);
-#pragma unroll
-                        for (int e8 = 0; e8 < 8; ++e8) fa[e8] += fb[e8];
-                        a.from_float(fa);
-                        v = a.v;
-                    }
-                }
-                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(gbase) + off) = v;
-            }
-        }
-    };
-    // 32 fp32 values of this thread's row (columns c0 .. c0+31) -> T -> global
-    auto emit32 = [&](void* gbase, const void* rbase, int c0, const float* v) {
-        if constexpr (sizeof(T) == 4) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint4 pk[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    pk[j] = make_uint4(__float_as_uint(v[h * 16 + 4 * j]), __float_as_uint(v[h * 16 + 4 * j + 1]), __float_as_uint(v[h * 16 + 4 * j + 2]),
-                                       __float_as_uint(v[h * 16 + 4 * j + 3]));
-                write_out(gbase, rbase, c0 + h * SCOLS, pk);
-            }
-        } else {
-            uint4 pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                Vec16<T> u;
-                u.from_float(v + 8 * j);
-                pk[j] = u.v;
-            }
-            write_out(gbase, rbase, c0, pk);
-        }
-    };
-    // y = (acc + bias) * row_scale for the 32 columns starting at c0
-    auto finish_y = [&](int c0, float* v) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const float4 b = bias4[c0 / 4 + g];
-            v[4 * g] = (v[4 * g] + b.x) * rs;
-            v[4 * g + 1] = (v[4 * g + 1] + b.y) * rs;
-            v[4 * g + 2] = (v[4 * g + 2] + b.z) * rs;
-            v[4 * g + 3] = (v[4 * g + 3] + b.w) * rs;
-        }
-    };
-    auto load_acc = [&](int c0, float* v) {  // hi*hi + cross terms, summed in round-to-nearest fp32 (see tmem_combine)
-        tmem_ld32(t_row + c0, v);
-        if (TF32 && p.nacc != 0) {  // (nacc == 0: dev probe, every product accumulated in one region)
-            float w[32];
-            tmem_ld32(t_row + p.Npad + c0, w);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += w[j];
-        }
-    };
-    float mean = 0.f, rstd = 1.f;
-    // ---- pass 1: y written back to region 0, row sum, pre-activation tensor ----
-    if (y_in_tmem) {
-        float s = 0.f;
-        for (int g = 0; g < n32; ++g) {
-            const int c0 = g * 32;
-            float v[32];
-            load_acc(c0, v);
-            finish_y(c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s += v[j];
-            tmem_st32_nowait(t_row + c0, v);
-            if (p.pre_out) emit32(p.pre_out, nullptr, c0, v);
-        }
-        tmem_st_wait();
-        mean = s / (float)H;
-    }
-    // ---- pass 2: variance around the mean (two-pass, like torch) ----
-    if (ln) {
-        float qs = 0.f;
-        for (int g = 0; g < n32; ++g) {
-            float v[32];
-            tmem_ld32(t_row + g * 32, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float d = v[j] - mean;
-                qs = fmaf(d, d, qs);
-            }
-        }
-        rstd = rsqrtf(qs / (float)H + p.eps);
-        if (p.ln_stats && rok) {
-            p.ln_stats[2 * row] = mean;
-            p.ln_stats[2 * row + 1] = rstd;
-        }
-    }
-    // ---- pass 3: normalise, ReLU, dropout, row-dot, (+ residual in the write-back), store ----
-    float dot = 0.f;
-    for (int g = 0; g < n32; ++g) {
-        const int c0 = g * 32;
-        float v[32];
-        if (y_in_tmem) {
-            tmem_ld32(t_row + c0, v);
-        } else {
-            load_acc(c0, v);
-            finish_y(c0, v);
-        }
-        if (ln) {
-#pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                const float4 ga = gam4[c0 / 4 + g4], be = bet4[c0 / 4 + g4];
-                v[4 * g4] = (v[4 * g4] - mean) * rstd * ga.x + be.x;
-                v[4 * g4 + 1] = (v[4 * g4 + 1] - mean) * rstd * ga.y + be.y;
-                v[4 * g4 + 2] = (v[4 * g4 + 2] - mean) * rstd * ga.z + be.z;
-                v[4 * g4 + 3] = (v[4 * g4 + 3] - mean) * rstd * ga.w + be.w;
-            }
-        }
-        if (relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (drop) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t bits = dropout_bits(row_key, (uint32_t)(c0 + j));
-                v[j] = bits >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
-            }
-        }
-        if (p.rowdot_out) {
-#pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                const float4 w = rdw4[c0 / 4 + g4];
-                dot = fmaf(v[4 * g4], w.x, dot);
-                dot = fmaf(v[4 * g4 + 1], w.y, dot);
-                dot = fmaf(v[4 * g4 + 2], w.z, dot);
-                dot = fmaf(v[4 * g4 + 3], w.w, dot);
-            }
-        }
-        if (p.out) emit32(p.out, p.residual, c0, v);
-    }
-    if (p.rowdot_out && rok) p.rowdot_out[row] = dot + (p.rowdot_b ? __ldg(p.rowdot_b) : 0.f);
-}
-
-// Lean form of epilogue_tile for k_linear_tcp (same arithmetic, same staging layout).  tools/lin_knock.py + the ncu source page
-// showed the epilogue warps, not the main loop, pacing the persistent kernel (epilogue alone 114 us of the 134 us SAGE forward;
+// Written lean on purpose: tools/lin_knock.py + the ncu source page showed the epilogue warps, not the main loop, pacing the
+// persistent kernel (epilogue alone 114 us of the 134 us SAGE forward;
 // main loop alone 77 us): ~6.4k warp instructions per tile and warp at ~0.2 IPC, a third of them address / predicate / branch
 // overhead of the write-back (64-bit row bound checks and a reconvergence region per store, register copies of the prefetched
 // residual, special registers re-read per round), and a quarter of the stall samples on the residual loads, requested one
 // 64-byte round (~200 clk) ahead.  Here: FULL tiles carry no row predicates, every address is a per-tile lane pointer plus
 // compile-time multiples of one step, the residual of a whole 32-column group is requested BEFORE the group's TMEM load and
-// math (no copies: each round owns its registers), and main + cross accumulators are loaded with one wait.
+// math (no copies: each round owns its registers), and main + cross accumulators are loaded with one wait
+// (fp32 SAGE forward 134 -> 118 us, bf16 H = 256 on 2 M rows 1129 -> 986 us).
 template <typename T, bool TF32, bool FULL>
-__device__ __forceinline__ void epilogue_tile2(const Args& p, const float* cvec, int HP, uint8_t* slice, uint32_t t_row, int64_t m_base, int q, int lane) {
+__device__ __forceinline__ void epilogue_tile(const Args& p, const float* cvec, int HP, uint8_t* slice, uint32_t t_row, int64_t m_base, int q, int lane) {
     constexpr int SCOLS = 64 / (int)sizeof(T);  // columns per 64-byte staging round: 16 fp32 / 32 bf16
     constexpr int ROUNDS = 32 / SCOLS;          // rounds per 32-column group
     constexpr int EPS = 16 / (int)sizeof(T);    // elements per 16-byte slot
@@ -1181,8 +974,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_linear_tcp(const __grid_consta
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * buf_cols;
 
             if (!(p.knock & 8)) {
-                if (m_base + kTileM <= p.N) epilogue_tile2<T, TF32, true>(p, cvec, HP, slice, t_row, m_base, q, lane);
-                else epilogue_tile2<T, TF32, false>(p, cvec, HP, slice, t_row, m_base, q, lane);
+                if (m_base + kTileM <= p.N) epilogue_tile<T, TF32, true>(p, cvec, HP, slice, t_row, m_base, q, lane);
+                else epilogue_tile<T, TF32, false>(p, cvec, HP, slice, t_row, m_base, q, lane);
             }
             fence_tc_before();
             __syncwarp();
@@ -1448,7 +1241,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1) k_line
             mbar_wait(&acc_full[ab], (uint32_t)((i >> 1) & 1));
             fence_tc_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * buf_cols;
-            epilogue_tile<T, TF32>(p, cvec, HP, slice, t_row, m_base, q, lane);
+            if (m_base + kTileM <= p.N) epilogue_tile<T, TF32, true>(p, cvec, HP, slice, t_row, m_base, q, lane);
+            else epilogue_tile<T, TF32, false>(p, cvec, HP, slice, t_row, m_base, q, lane);
             fence_tc_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)ab);
