@@ -655,11 +655,21 @@ def main():
     with torch.no_grad():
         for i in range(3):
             model(resident[i % n_batches].x, graphs[i % n_batches])
-        ms_inf = timed_region(lambda i: model(resident[(warmup + i) % n_batches].x, graphs[(warmup + i) % n_batches]), steps,
-                              dist_on, device)
+        if not args.no_graph:  # one CUDA graph per resident batch, like the training arm: 13 launches per forward are host-bound otherwise
+            from deep_fem_uav_wing.gnn.graphed import GraphedForward
+
+            fwd = GraphedForward(model)
+            ireplays = [fwd.capture_resident(b.x, g_)[0] for b, g_ in zip(resident, graphs)]
+            for r_ in ireplays[:3]:
+                r_()
+            ms_inf = timed_region(lambda i: ireplays[(warmup + i) % n_batches](), steps, dist_on, device)
+        else:
+            ms_inf = timed_region(lambda i: model(resident[(warmup + i) % n_batches].x, graphs[(warmup + i) % n_batches]), steps,
+                                  dist_on, device)
     model.train()
     infer = {"value": BATCH * steps * world / (ms_inf * 1e-3), "unit": "meshes/s", "ms_per_step": ms_inf / steps,
-             "nodes_per_sec": BATCH * steps * world * NODES / (ms_inf * 1e-3), "what": "eval-mode forward, device-resident batches, CSR cached"}
+             "nodes_per_sec": BATCH * steps * world * NODES / (ms_inf * 1e-3), "cuda_graph": not args.no_graph,
+             "what": "eval-mode forward, device-resident batches, CSR cached"}
 
     # ---- roofline pass: same steps with per-launch CUDA events ---------------------------------
     prof_steps = min(steps, 8)

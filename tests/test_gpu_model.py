@@ -244,7 +244,7 @@ def test_prefetching_loader_matches_host_collation():
 def test_cuda_graph_training_step_matches_eager():
     """GraphedTrainStep (capture of fwd + loss + bwd + AdamW incl. the CSR build) must follow the eager trajectory
     exactly with dropout off, and draw a different dropout mask on every replay with dropout on."""
-    from deep_fem_uav_wing.gnn import synth
+    from deep_fem_uav_wing.gnn import ops, synth
     from deep_fem_uav_wing.gnn.graphed import GraphedForward, GraphedTrainStep
 
     GraphSAGEModel, MaskedMSELoss, _, _ = _models()
@@ -297,6 +297,15 @@ def test_cuda_graph_training_step_matches_eager():
         for _ in range(2):
             assert rel_max(gf(x, ei2), model(x, ei2)) < TOL_FP32
             assert rel_max(gf(x, ei), model(x, ei)) < TOL_FP32
+        # resident form: captured on the caller's tensors with a prebuilt CSR; a replay sees new contents of x
+        g = ops.get_graph(ei, x.shape[0])
+        xr = x.clone()
+        replay, out = gf.capture_resident(xr, g)
+        replay()
+        assert torch.equal(out, model(xr, g))
+        xr.mul_(0.5)
+        replay()
+        assert torch.equal(out, model(xr, g))
 
 
 @pytest.mark.gpu
