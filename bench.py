@@ -333,7 +333,9 @@ def aggregation_cfg4(device, pk, iters=20):
         x = torch.randn(n, H, device=device, generator=torch.Generator(device=device).manual_seed(1)).bfloat16()
         amin = 2 * n * H * 2 + 4 * E + 4 * (n + 1)
         ent = {"N": n, "E": E, "A_min_MB": round(amin / 1e6, 1), "A_gather_MB": round((E * H * 2 + n * H * 2 + 4 * E + 4 * (n + 1)) / 1e6, 1)}
-        for name, (fn, info) in ops.cfg4_aggregation_paths(ei, n, pos_n, x).items():
+        # the path the model takes is timed FIRST: timed right behind the slow comparison paths (2.1 / 2.8 ms per launch on the randomly
+        # numbered lattice, 60+ launches) the same kernel measured 600-625 us instead of 495-503 us (tools/cfg4_random_probe.py)
+        for name, (fn, info) in reversed(list(ops.cfg4_aggregation_paths(ei, n, pos_n, x).items())):
             if os.environ.get("DFW_BENCH_VERBOSE"):
                 print(f"[cfg4] {order} {name}", file=sys.stderr, flush=True)
             for _ in range(3):

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import os
 from collections import OrderedDict
+import dataclasses
 from dataclasses import dataclass, field
 
 import torch
@@ -532,9 +533,10 @@ def get_inference_graph(edge_index: torch.Tensor, num_nodes: int, pos: torch.Ten
     if ig is not None and ig.graph is not None and (ig.graph.edge_index is edge_index or ig.new_id is not None):
         _INF_CACHE.move_to_end(key)
         return ig
-    g = get_graph(edge_index, num_nodes)
-    if g.plan is None:
-        g.plan = build_agg_plan(g.rowptr, g.col, num_nodes)
+    # the plan lives on a COPY of the cached CSR: ops.get_graph(edge_index) - what every other caller of this mesh gets -
+    # must stay a plain graph (SageConvFn takes the block kernel whenever its graph carries a profitable plan)
+    g = dataclasses.replace(get_graph(edge_index, num_nodes), _pending=[])
+    g.plan = build_agg_plan(g.rowptr, g.col, num_nodes)
     ok = g.plan.check()
     ig = InferenceGraph(g, None, None, g.plan.staged_rows_per_row, g.plan.staged_rows_per_row)
     want = reorder == "always" or (reorder == "auto" and (not ok or g.plan.staged_rows_per_row > TC_AGG_REORDER_ABOVE))
@@ -574,7 +576,6 @@ def cfg4_aggregation_paths(edge_index, num_nodes, pos, x):
             paths["tensor_core_blocks"] = (lambda: aggregate_tc(plan, g.inv_deg, x, g.num_edges),
                                            {"what": "dfw_sage_aggregate_tc, given numbering", "staged_rows_per_row": round(plan.staged_rows_per_row, 3),
                                             "one_time_plan_ms": round(t_plan * 1e3, 2)})
-        g.plan = plan
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ig = get_inference_graph(edge_index, num_nodes, pos=pos, reorder="auto")
@@ -957,7 +958,7 @@ class SageConvFn(_Fn):
         dt = x.dtype
         wl, wr = _w(w_l, dt), _w(w_r, dt)
         bl = _f32(b_l.detach()) if b_l is not None else None
-        agg = aggregate(graph.rowptr, graph.col, graph.inv_deg, x)
+        agg = aggregate_mean(graph, x)  # the tensor-core block kernel when the graph carries a profitable plan (large-mesh bf16 inference)
         # needs_input_grad reflects requires_grad even under torch.no_grad(): without the grad-mode test eval / predict()
         # would still write the pre-LayerNorm tensor and the statistics of every layer
         needs_grad = _caller_grad_enabled() and any(ctx.needs_input_grad[:6])

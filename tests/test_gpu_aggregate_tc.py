@@ -150,9 +150,13 @@ def test_large_mesh_inference_path_relabels_nodes_and_matches_the_plain_path(ops
     torch.manual_seed(5)
     model = GraphSAGEModel(10, 128, 1, 2, dropout=0.0).cuda().eval().set_compute_dtype(torch.bfloat16)
     monkeypatch.setattr(ops, "TC_AGG_MIN_NODES", 1000)
-    k0 = ops.LAUNCH_COUNTER["kernels"]
+    monkeypatch.setattr(ops, "TC_AGG_MIN_REUSE", 0.0)  # (the policy would leave a 120k-node mesh with ~4.5 staged rows per row to the gather kernel)
+    tc_calls = []
+    real_tc = ops.aggregate_tc
+    monkeypatch.setattr(ops, "aggregate_tc", lambda *a, **k: (tc_calls.append(1), real_tc(*a, **k))[1])
     with torch.no_grad():
         out_plan = model(x, ei)
+    assert len(tc_calls) == 2, "every SAGE layer of the large-mesh path must run the tensor-core block aggregation"
     ig = ops.get_inference_graph(ei, n, pos=x[:, :3], reorder="auto")
     assert ig.order is not None and ig.graph.plan.usable
     assert ig.staged_rows_per_row_given > 8 and ig.staged_rows_per_row < 4.8  # random numbering -> compact blocks
@@ -161,6 +165,7 @@ def test_large_mesh_inference_path_relabels_nodes_and_matches_the_plain_path(ops
     monkeypatch.setattr(ops, "TC_AGG_MIN_NODES", 10 ** 12)
     with torch.no_grad():
         out_plain = model(x, ei)
+    assert len(tc_calls) == 2  # the plain path stays on the gather kernel
     assert out_plan.shape == out_plain.shape == (n, 1)
     err = rel_max(out_plan.float().cpu(), out_plain.float().cpu())
     record("large_mesh_inference_path_vs_plain", rel_max=err)
