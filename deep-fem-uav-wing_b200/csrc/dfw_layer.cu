@@ -217,3 +217,96 @@ extern "C" int dfw_mlp2_bwd(const void* x, const void* hidden, const void* out, 
     if (!g_x) return 0;
     return dfw_linear_bwd_input(g1, w1, nullptr, nullptr, g_x, N, Hmid, K, dtype, base + w.o_lin, dfw_linear_ws_bytes(K, Hmid, 0, dtype), stream);
 }
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// One-call inference forward of the whole model (reference model.py:74-99 in eval mode; the loop body of inference_gnn.py:224-328):
+// encoder MLP, L x (mean aggregation + fused SAGE linear with LayerNorm / ReLU / residual), decoder MLP with the 64 -> 1 row dot -
+// the same launches gnn/model.py issues one Python call at a time (13 calls, ~0.5-0.8 ms of host time per forward: the config-5
+// screening loop was host bound), behind one C call.  Bit-identical to the piecewise path.
+// Workspace: [first-layer fp32 result (mixed mode) | mid | h_a | h_b | agg | linear workspace], all 256-byte aligned.
+// ------------------------------------------------------------------------------------------------------------------------------
+namespace dfw {
+namespace {
+struct FwdWs {
+    size_t o_mid32, o_mid, o_ha, o_hb, o_agg, o_lin, lin_bytes, total;
+};
+FwdWs carve_forward(int64_t N, int64_t in_dim, int64_t enc_mid, int64_t H, int64_t dec_mid, int x_dtype, int dtype) {
+    const size_t e = dtype == DFW_F32 ? 4 : 2;
+    FwdWs w{};
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+    const bool mixed = x_dtype == DFW_F32 && dtype != DFW_F32;
+    w.o_mid32 = take(mixed ? (size_t)N * enc_mid * 4 : 0);
+    w.o_mid = take((size_t)N * enc_mid * e);
+    w.o_ha = take((size_t)N * H * e);
+    w.o_hb = take((size_t)N * H * e);
+    w.o_agg = take((size_t)N * H * e);
+    w.lin_bytes = std::max({dfw_linear_ws_bytes(enc_mid, in_dim, 0, mixed ? DFW_F32 : dtype), dfw_linear_ws_bytes(H, enc_mid, 0, dtype),
+                            dfw_linear_ws_bytes(H, H, H, dtype), dfw_linear_ws_bytes(dec_mid, H, 0, dtype)});
+    w.o_lin = take(w.lin_bytes);
+    w.total = off + 256;
+    return w;
+}
+}  // namespace
+}  // namespace dfw
+
+extern "C" size_t dfw_graphsage_forward_ws_bytes(int64_t N, int64_t in_dim, int64_t enc_mid, int64_t hidden, int64_t dec_mid, int x_dtype,
+                                                 int dtype) {
+    if (N < 0 || in_dim < 1 || enc_mid < 1 || hidden < 1 || dec_mid < 1) return 0;
+    return dfw::carve_forward(N, in_dim, enc_mid, hidden, dec_mid, x_dtype, dtype).total;
+}
+
+extern "C" int dfw_graphsage_forward(const int32_t* rowptr, const int32_t* col, const float* inv_deg, const void* x, int x_dtype,
+                                     const void* const* weights, int num_layers, int64_t N, int64_t E, int64_t in_dim, int64_t enc_mid,
+                                     int64_t hidden, int64_t dec_mid, float ln_eps, int dtype, float* out, void* ws, size_t ws_bytes,
+                                     dfw_stream_t stream) {
+    using namespace dfw;
+    DFW_REQUIRE(x && weights && out && rowptr && inv_deg, "dfw_graphsage_forward: null pointer");
+    DFW_REQUIRE(num_layers >= 0 && N >= 0, "dfw_graphsage_forward: bad sizes");
+    DFW_REQUIRE(dtype == DFW_F32 || dtype == DFW_BF16, "dfw_graphsage_forward: dtype must be DFW_F32 or DFW_BF16");
+    DFW_REQUIRE(x_dtype == DFW_F32 || x_dtype == dtype, "dfw_graphsage_forward: features are fp32 or in the compute dtype");
+    const FwdWs w = carve_forward(N, in_dim, enc_mid, hidden, dec_mid, x_dtype, dtype);
+    DFW_REQUIRE(ws && ws_bytes >= w.total, "dfw_graphsage_forward: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    const int nw = 8 + 5 * num_layers;
+    for (int i = 0; i < nw; ++i) {
+        const bool optional = (i == 1 || i == 3 || i == nw - 3 || i == nw - 1) || (i >= 4 && i < nw - 4 && (i - 4) % 5 == 1);  // biases
+        DFW_REQUIRE(weights[i] || optional, "dfw_graphsage_forward: weights[%d] is NULL", i);
+    }
+    if (N == 0) return 0;
+    char* b = base256(ws);
+    void* lin = b + w.o_lin;
+    const bool mixed = x_dtype == DFW_F32 && dtype != DFW_F32;
+    void* mid = b + w.o_mid;
+    // encoder (model.py:52-57): the first linear reads the raw features in THEIR dtype (see gnn/model.py), its output enters the compute dtype
+    int rc;
+    if (mixed) {
+        void* mid32 = b + w.o_mid32;
+        rc = dfw_linear_fwd(x, weights[0], in_dim, nullptr, nullptr, 0, (const float*)weights[1], nullptr, nullptr, 1e-5f, nullptr, 0.f, 0, mid32, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, N, enc_mid, DFW_EP_RELU, DFW_F32, lin, w.lin_bytes, stream);
+        if (rc) return rc;
+        rc = dfw_cast(mid32, DFW_F32, mid, dtype, N * enc_mid, stream);
+    } else {
+        rc = dfw_linear_fwd(x, weights[0], in_dim, nullptr, nullptr, 0, (const float*)weights[1], nullptr, nullptr, 1e-5f, nullptr, 0.f, 0, mid, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, N, enc_mid, DFW_EP_RELU, dtype, lin, w.lin_bytes, stream);
+    }
+    if (rc) return rc;
+    void* h = b + w.o_ha;
+    void* h2 = b + w.o_hb;
+    void* agg = b + w.o_agg;
+    rc = dfw_linear_fwd(mid, weights[2], enc_mid, nullptr, nullptr, 0, (const float*)weights[3], nullptr, nullptr, 1e-5f, nullptr, 0.f, 0, h, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, N, hidden, DFW_EP_RELU, dtype, lin, w.lin_bytes, stream);
+    if (rc) return rc;
+    // SAGE layers (model.py:89-95, eval: no dropout, nothing saved)
+    for (int l = 0; l < num_layers; ++l) {
+        const void* const* lw = weights + 4 + 5 * l;
+        rc = dfw_sage_layer_fwd(rowptr, col, inv_deg, h, lw[0], (const float*)lw[1], lw[2], (const float*)lw[3], (const float*)lw[4], ln_eps, 0.f, 0,
+                                DFW_EP_LAYERNORM | DFW_EP_RELU | DFW_EP_RESIDUAL, agg, nullptr, nullptr, h2, N, E, hidden, hidden, dtype, lin, w.lin_bytes,
+                                stream);
+        if (rc) return rc;
+        std::swap(h, h2);
+    }
+    // decoder (model.py:67-72, out_channels = 1): Linear -> ReLU -> (dropout off) -> Linear(dec_mid, 1) as the epilogue's row dot
+    const void* const* dw = weights + 4 + 5 * num_layers;
+    return dfw_mlp2_fwd(h, dw[0], (const float*)dw[1], dw[2], (const float*)dw[3], 0.f, 0, 0, DFW_MLP2_DECODER, nullptr, out, N, hidden, dec_mid, 1, dtype, lin,
+                        w.lin_bytes, stream);
+}

@@ -33,6 +33,9 @@ SIGNATURES = {
     "dfw_node_features_batched_ws_bytes": (c_size_t, [c_int64]),
     "dfw_node_features_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                           c_void_p, c_size_t, c_void_p]),
+    "dfw_graphsage_forward_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
+    "dfw_graphsage_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(c_void_p), c_int, c_int64, c_int64, c_int64,
+                                      c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dfw_sage_aggregate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                    c_int, c_void_p]),
     "dfw_sage_aggregate_scaled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,

@@ -91,6 +91,8 @@ class GraphSAGEModel(nn.Module):
         self.dropout = dropout
         self.compute_dtype = torch.float32
         self.node_reorder = "auto"  # 'auto' | 'always' | 'never': k-d relabelling of large meshes for bf16 inference (ops.get_inference_graph)
+        self.mesh_plan = "auto"  # large-mesh bf16 inference: prepare the mesh for the block aggregation 'always', 'never', or ('auto') from
+        #                          the second forward on the same edge_index tensor - a graph seen once is not worth the one-time preparation
         self.device_seeds = None  # int64 CUDA tensor [num_layers + 1]: dropout seeds read by the kernels (CUDA-graph mode)
 
         self.encoder = nn.Sequential(
@@ -124,7 +126,8 @@ class GraphSAGEModel(nn.Module):
         n_nodes = int(x.shape[0])
         if (cd == torch.bfloat16 and not torch.is_grad_enabled() and isinstance(edge_index, torch.Tensor)
                 and self.hidden_channels in ops.TC_AGG_WIDTHS and n_nodes >= ops.TC_AGG_MIN_NODES
-                and not torch.cuda.is_current_stream_capturing()):
+                and not torch.cuda.is_current_stream_capturing() and self.mesh_plan != "never"
+                and (self.mesh_plan == "always" or ops.static_mesh_seen_before(edge_index))):
             # large static mesh, bf16 inference (BASELINE.json config 4): block plan for the tensor-core aggregation and,
             # where the given numbering has poor locality, a one-time k-d relabelling of the nodes - applied here to the
             # 10-wide input and undone on the 1-wide output, so no [N, H] tensor is ever permuted
@@ -136,6 +139,13 @@ class GraphSAGEModel(nn.Module):
                 restore = ig.new_id
         else:
             graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, n_nodes)
+        if (not torch.is_grad_enabled() and not self.training and self.out_channels == 1 and graph.plan is None
+                and x.dtype in (torch.float32, cd)):
+            # inference: the whole forward behind one C call (dfw_graphsage_forward) - the same launches as below, bit-identical,
+            # without ~0.5 ms of Python between them (graphs with a block plan keep the piecewise path: its aggregation differs)
+            out = ops.graphsage_forward(graph, x, self._forward_weights(x.dtype, cd), cd, float(self.norms[0].eps) if self.num_layers else 1e-5)
+            out = ops.cast(ops.cast(out, cd), out_dtype)  # (the piecewise path hands the decoder's fp32 row dot over in the compute dtype)
+            return out if restore is None else out.index_select(0, restore)
         p = float(self.dropout) if self.training else 0.0
         if p > 0.0 and self.device_seeds is not None:  # seeds live on the device (see gnn/graphed.py)
             layer_seed = [self.device_seeds[i:i + 1] for i in range(self.num_layers)]
@@ -166,6 +176,25 @@ class GraphSAGEModel(nn.Module):
             out = ops.LinearFn.apply(hid, dec3.weight, dec3.bias, False, 0.0, 0)
         out = ops.cast_ad(out, out_dtype)
         return out if restore is None else out.index_select(0, restore)
+
+    def _forward_weights(self, x_dtype: torch.dtype, cd: torch.dtype) -> "ops.ForwardWeights":
+        """Parameters in the layout of ``dfw_graphsage_forward`` (compute-dtype copies of the matrices), rebuilt only when a parameter
+        was modified or replaced since the last call."""
+        params = list(self.parameters())
+        key = (x_dtype, cd, tuple((q.data_ptr(), q._version) for q in params))
+        cached = getattr(self, "_fw_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        f32 = lambda t: ops._f32(t.detach()) if t is not None else None  # noqa: E731
+        enc0, enc2 = self.encoder[0], self.encoder[2]
+        ts = [ops._w(enc0.weight, x_dtype if x_dtype == torch.float32 else cd), f32(enc0.bias), ops._w(enc2.weight, cd), f32(enc2.bias)]
+        for conv, norm in zip(self.convs, self.norms):
+            ts += [ops._w(conv.lin_l.weight, cd), f32(conv.lin_l.bias), ops._w(conv.lin_r.weight, cd), f32(norm.weight), f32(norm.bias)]
+        dec0, dec3 = self.decoder[0], self.decoder[3]
+        ts += [ops._w(dec0.weight, cd), f32(dec0.bias), f32(dec3.weight).reshape(-1), f32(dec3.bias).reshape(-1) if dec3.bias is not None else None]
+        fw = ops.ForwardWeights(ts, (self.in_channels, int(enc0.out_features), self.hidden_channels, int(dec0.out_features), self.num_layers))
+        object.__setattr__(self, "_fw_cache", (key, fw))
+        return fw
 
     def predict(self, data):
         """Convenience method for inference (``model.py:101-112``)."""

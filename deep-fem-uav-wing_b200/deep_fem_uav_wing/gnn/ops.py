@@ -6,9 +6,11 @@ arithmetic step of the GraphSAGE path is a hand-written sm_100a kernel reached t
 """
 from __future__ import annotations
 
-import os
-from collections import OrderedDict
+import ctypes
 import dataclasses
+import os
+import weakref
+from collections import OrderedDict
 from dataclasses import dataclass, field
 
 import torch
@@ -127,6 +129,7 @@ class CSRGraph:
     skipped_faces: torch.Tensor | None = None
     status_t: torch.Tensor | None = None  # int32 [3] of dfw_csr_transpose ([2] = 1: the graph was not symmetric)
     plan: "AggPlan | None" = None         # block plan for dfw_sage_aggregate_tc (large-mesh bf16 inference)
+    edge_count: torch.Tensor | None = None  # int64 [1] on the device: exact E of a graph built with faces_to_graph(sync=False)
 
     def transpose(self):
         if self.rowptr_t is None:
@@ -189,13 +192,19 @@ def csr_transpose_raw(edge_index: torch.Tensor, num_nodes: int, rowptr: torch.Te
     return rowptr_t, col_t, status
 
 
-def faces_to_graph(faces: torch.Tensor, num_nodes: int, node_ids: torch.Tensor | None = None, want_edge_index: bool = True):
+def faces_to_graph(faces: torch.Tensor, num_nodes: int, node_ids: torch.Tensor | None = None, want_edge_index: bool = True,
+                   sync: bool = True):
     """Triangle faces -> (CSRGraph, edge_index) on the device (``dfw_faces_to_csr``; reference
     ``_faces_to_edge_index``, ``dataset.py:26-63``).
 
     ``faces``: int64 [F,3] of node ids; ``node_ids``: int64 [N] ids in node order (``npz["node_id"]``,
     ``dataset.py:94``), or None when the faces already hold 0-based indices.  One 8-byte D2H read (the edge count).
-    The returned ``edge_index`` is registered with the graph cache, so ``model(x, edge_index)`` does not rebuild."""
+    The returned ``edge_index`` is registered with the graph cache, so ``model(x, edge_index)`` does not rebuild.
+    ``sync=False`` (inference graphs, ``want_edge_index=False``): no D2H read at all - ``col`` keeps its capacity of 6F entries
+    (``rowptr`` delimits the valid ones), ``num_edges`` is the closed-surface estimate 3F (the kernels use it as a sizing hint
+    only) and the exact count stays on the device in ``graph.edge_count`` - so a screening loop never waits for the GPU."""
+    if not sync and want_edge_index:
+        raise ValueError("faces_to_graph(sync=False) cannot size edge_index: pass want_edge_index=False")
     _require_cuda(faces, "faces")
     if faces.dtype != torch.int64:
         raise TypeError(f"faces must be int64, got {faces.dtype}")
@@ -227,10 +236,14 @@ def faces_to_graph(faces: torch.Tensor, num_nodes: int, node_ids: torch.Tensor |
                                    inv_deg.data_ptr(), _ptr(ei), nedges.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes,
                                    _stream(f)))
     LAUNCH_COUNTER["kernels"] += 13
-    E = int(nedges.item())
-    col = col[:E]
+    if sync:
+        E = int(nedges.item())
+        col = col[:E]
+    else:
+        E = min(3 * F, cap)
     edge_index = ei[:, :E].contiguous() if ei is not None else None
     g = CSRGraph(edge_index, N, E, rowptr, col, inv_deg, None, status[:2])
+    g.edge_count = nedges
     g.rowptr_t, g.col_t = rowptr, col  # both directions of every edge are present: the transpose is the graph itself
     g.skipped_faces = status[2:3]
     if edge_index is not None:
@@ -521,6 +534,24 @@ class InferenceGraph:
 
 
 _INF_CACHE: "OrderedDict[tuple, InferenceGraph]" = OrderedDict()
+
+
+_SEEN_MESHES: "OrderedDict[int, weakref.ref]" = OrderedDict()
+
+
+def static_mesh_seen_before(edge_index: torch.Tensor) -> bool:
+    """True from the SECOND call with the same ``edge_index`` tensor object.  Preparing a mesh for the block aggregation (plan,
+    k-d relabelling: ~100 ms for 2 M nodes, two small D2H reads) pays only when the mesh is used again; a screening loop that
+    sees every graph once (BASELINE.json config 5) must not pay it per launch."""
+    k = id(edge_index)
+    r = _SEEN_MESHES.get(k)
+    if r is not None and r() is edge_index:
+        _SEEN_MESHES.move_to_end(k)
+        return True
+    _SEEN_MESHES[k] = weakref.ref(edge_index)
+    while len(_SEEN_MESHES) > 16:
+        _SEEN_MESHES.popitem(last=False)
+    return False
 
 
 def get_inference_graph(edge_index: torch.Tensor, num_nodes: int, pos: torch.Tensor | None = None, reorder: str = "auto") -> InferenceGraph:
@@ -820,6 +851,33 @@ def sage_layer_bwd(graph: "CSRGraph", x, agg, pre, stats, w_l, w_r, ln, g_out, d
                                      ws.data_ptr(), ws_bytes, _stream(x)))
     LAUNCH_COUNTER["kernels"] += 7 if want_input_grad else 4
     return g_x, dw_l, db_l, dw_r, dgamma, dbeta
+
+
+class ForwardWeights:
+    """The model's parameters as ``dfw_graphsage_forward`` takes them: a host array of device pointers (matrices in the compute
+    dtype, vectors fp32) plus the tensors that keep those pointers alive.  Built by ``GraphSAGEModel`` and cached there until a
+    parameter changes."""
+
+    def __init__(self, tensors: list, dims: tuple):
+        self.tensors = tensors  # order: see include/dfw_b200.h
+        self.array = (ctypes.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else None) for t in tensors])
+        self.in_dim, self.enc_mid, self.hidden, self.dec_mid, self.num_layers = dims
+
+
+def graphsage_forward(graph: "CSRGraph", x, weights: ForwardWeights, compute_dtype: torch.dtype, eps: float = 1e-5) -> torch.Tensor:
+    """``dfw_graphsage_forward``: the whole eval-mode forward (``model.py:74-99``) in ONE C call -> fp32 ``[N, 1]``."""
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    N, dev = int(x.shape[0]), x.device
+    out = torch.empty(N, 1, dtype=torch.float32, device=dev)
+    ws_bytes = lib.dfw_graphsage_forward_ws_bytes(N, weights.in_dim, weights.enc_mid, weights.hidden, weights.dec_mid, _dt(x), _DTYPES[compute_dtype])
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dfw_graphsage_forward(graph.rowptr.data_ptr(), _ptr(graph.col), graph.inv_deg.data_ptr(), x.data_ptr(), _dt(x), weights.array,
+                                        weights.num_layers, N, graph.num_edges, weights.in_dim, weights.enc_mid, weights.hidden, weights.dec_mid,
+                                        float(eps), _DTYPES[compute_dtype], out.data_ptr(), ws.data_ptr(), ws_bytes, _stream(x)))
+    LAUNCH_COUNTER["kernels"] += 3 + 2 * weights.num_layers + (1 if (x.dtype == torch.float32 and compute_dtype != torch.float32) else 0)
+    return out
 
 
 MLP2_ENCODER, MLP2_DECODER = 0, 1

@@ -303,6 +303,26 @@ int dfw_stress_metrics(const void* pred, const void* target, const uint8_t* mask
 /* dtype conversion helper (weights fp32 -> bf16 copies for the bf16 path) */
 int dfw_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, dfw_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One-call inference forward of the whole model (model.py:74-99 in eval mode; the per-case body of
+ * inference_gnn.py:224-328): encoder MLP, num_layers x [mean aggregation + fused SAGE linear with LayerNorm, ReLU,
+ * residual], decoder MLP whose Linear(dec_mid, 1) is the epilogue's row dot.  The launches of the entry points above
+ * behind ONE call (a Python host spends 0.5-0.8 ms per forward issuing them one by one); bit-identical to the pieces.
+ *   x [N,in_dim] in x_dtype: DFW_F32 features are read as they are by the first linear (its weight then fp32 too),
+ *   even when the compute dtype is bf16.   out: fp32 [N].
+ *   weights: HOST array of 8 + 5*num_layers DEVICE pointers, matrices [out,in] row-major in the compute dtype
+ *   (weights[0] in x_dtype), vectors fp32:
+ *     [0..3]  encoder: W0 [enc_mid,in_dim], b0 [enc_mid], W1 [hidden,enc_mid], b1 [hidden]
+ *     [4+5l..] layer l: lin_l.weight [hidden,hidden], lin_l.bias [hidden], lin_r.weight, LayerNorm weight, LayerNorm bias
+ *     [last 4] decoder: W0 [dec_mid,hidden], b0 [dec_mid], w1 fp32 [dec_mid], b1 fp32 [1]      (biases nullable)
+ * ---------------------------------------------------------------------------------------- */
+size_t dfw_graphsage_forward_ws_bytes(int64_t N, int64_t in_dim, int64_t enc_mid, int64_t hidden, int64_t dec_mid,
+                                      int x_dtype, int dtype);
+int dfw_graphsage_forward(const int32_t* rowptr, const int32_t* col, const float* inv_deg, const void* x, int x_dtype,
+                          const void* const* weights, int num_layers, int64_t N, int64_t E,
+                          int64_t in_dim, int64_t enc_mid, int64_t hidden, int64_t dec_mid, float ln_eps, int dtype,
+                          float* out, void* ws, size_t ws_bytes, dfw_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,6 +149,7 @@ def test_large_mesh_inference_path_relabels_nodes_and_matches_the_plain_path(ops
     x, ei = torch.from_numpy(mesh["x"]).cuda(), torch.from_numpy(mesh["edge_index"]).cuda()
     torch.manual_seed(5)
     model = GraphSAGEModel(10, 128, 1, 2, dropout=0.0).cuda().eval().set_compute_dtype(torch.bfloat16)
+    model.mesh_plan = "always"  # ('auto' prepares a mesh from its second forward on: covered at the end of this test)
     monkeypatch.setattr(ops, "TC_AGG_MIN_NODES", 1000)
     monkeypatch.setattr(ops, "TC_AGG_MIN_REUSE", 0.0)  # (the policy would leave a 120k-node mesh with ~4.5 staged rows per row to the gather kernel)
     tc_calls = []
@@ -176,6 +177,16 @@ def test_large_mesh_inference_path_relabels_nodes_and_matches_the_plain_path(ops
     with torch.no_grad():
         out_never = model(x, ei)
     assert rel_max(out_never.float().cpu(), out_plain.float().cpu()) < TOL_BF16
+    # 'auto': a mesh is prepared from its SECOND forward on (a screening loop sees every graph once)
+    model.mesh_plan, model.node_reorder = "auto", "auto"
+    ei_new = ei.clone()
+    n0 = len(tc_calls)
+    with torch.no_grad():
+        first = model(x, ei_new)
+        assert len(tc_calls) == n0
+        second = model(x, ei_new)
+        assert len(tc_calls) == n0 + 2
+    assert rel_max(first.float().cpu(), out_plain.float().cpu()) < TOL_BF16 and rel_max(second.float().cpu(), out_plain.float().cpu()) < TOL_BF16
 
 
 @pytest.mark.parametrize("order,reorder", [("native", "never"), ("random", "never"), ("random", "always")])

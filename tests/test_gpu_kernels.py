@@ -466,6 +466,13 @@ def test_faces_to_graph_on_a_config_sized_surface_mesh(ops):
     a = ops.aggregate(g.rowptr, g.col, g.inv_deg, x)
     g_host = ops.get_graph(torch.from_numpy(m["edge_index"]).cuda(), n)
     assert torch.equal(a, ops.aggregate(g_host.rowptr, g_host.col, g_host.inv_deg, x))
+    # sync=False: no host read - col keeps its capacity, num_edges is the closed-surface estimate, the exact count stays on the device
+    g2, none = ops.faces_to_graph(torch.from_numpy(m["faces"].astype(np.int64)).cuda(), n, want_edge_index=False, sync=False)
+    assert none is None and int(g2.edge_count.item()) == g.num_edges and g2.col.numel() >= g.num_edges
+    assert torch.equal(g2.rowptr, g.rowptr) and torch.equal(g2.col[: g.num_edges], g.col) and torch.equal(g2.inv_deg, g.inv_deg)
+    assert torch.equal(a, ops.aggregate(g2.rowptr, g2.col, g2.inv_deg, x))
+    with pytest.raises(ValueError):
+        ops.faces_to_graph(torch.from_numpy(m["faces"].astype(np.int64)).cuda(), n, sync=False)
 
 
 def test_node_features_batched_equals_per_case_calls(ops):

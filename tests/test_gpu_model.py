@@ -495,3 +495,38 @@ def test_loader_prebuilt_graph_and_graphed_step_follow_the_eager_trajectory():
     np.testing.assert_allclose(pre, eager, rtol=1e-5)
     for (k, a), b in zip(m_p.named_parameters(), m_e.parameters()):
         assert rel_l2(a, b) < 1e-5, k
+
+
+@pytest.mark.parametrize("cd", [torch.float32, torch.bfloat16])
+def test_one_call_inference_forward_is_bit_identical_to_the_piecewise_path(cd):
+    """eval + no_grad takes dfw_graphsage_forward (one C call for the whole model); with grad enabled the same model runs the
+    piecewise autograd path.  Same launches, same arguments: the predictions must be equal bit for bit.  A parameter update
+    must invalidate the cached weight table."""
+    from deep_fem_uav_wing.gnn import ops, synth
+
+    GraphSAGEModel, _, _, _ = _models()
+    m = synth.surface_tri_wing(5000, seed=11)
+    x, ei = torch.from_numpy(m["x"]).cuda(), torch.from_numpy(m["edge_index"]).cuda()
+    torch.manual_seed(3)
+    model = GraphSAGEModel(10, 128, 1, 3, dropout=0.1).cuda().eval().set_compute_dtype(cd)
+    calls = []
+    real = ops.graphsage_forward
+    ops.graphsage_forward = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+    try:
+        with torch.no_grad():
+            fast = model(x, ei)
+        assert len(calls) == 1
+        with torch.enable_grad():
+            slow = model(x, ei).detach()
+        assert len(calls) == 1
+        assert fast.shape == slow.shape == (x.shape[0], 1) and fast.dtype == slow.dtype
+        assert torch.equal(fast, slow)
+        with torch.no_grad():
+            for p_ in model.parameters():
+                p_.mul_(1.01)
+            fast2 = model(x, ei)
+        with torch.enable_grad():
+            slow2 = model(x, ei).detach()
+        assert torch.equal(fast2, slow2) and not torch.equal(fast2, fast)
+    finally:
+        ops.graphsage_forward = real
