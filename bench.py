@@ -592,6 +592,10 @@ def main():
 
     # ---- parity gates, printed with the perf numbers (rank 0; the oracle is the checker) ----------
     gates = parity_gates(device) if (rank == 0 and not args.no_cpu_baseline) else None
+    # The oracle above spins up torch's CPU intra-op pool (one OpenMP worker per core, busy-waiting between parallel regions); left
+    # that wide, those workers compete with the loader's prefetch thread for the host cores in the end-to-end arm (measured: e2e
+    # 1272 instead of 1540-1630 meshes/s).  The GPU arms need no CPU intra-op parallelism; the CPU arms set their own thread count.
+    torch.set_num_threads(1)
 
     # ---- data: this rank's shard of the 200 meshes (mesh id = rank + k*world) -----------------
     steps, warmup = args.steps, args.warmup
