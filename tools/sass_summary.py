@@ -51,7 +51,7 @@ def main():
     print("columns: instructions | tcgen05.mma (UTC*MMA) | tcgen05.commit (UTCBAR) | tcgen05.ld (LDTM) | tcgen05.st (STTM) | TMA load (UTMALDG) | TMA store (UTMASTG) | "
           "bulk copy (UBLKCP) | cp.async (LDGSTS) | mbarrier ops (SYNCS*) | legacy HMMA | resources\n")
     for (mangled, c), name in sorted(zip(kernels.items(), demangle), key=lambda t: t[1]):
-        short = re.sub(r"\(.*", "", name).replace("dfw::", "")
+        short = re.sub(r"\(.*", "", name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")).replace("dfw::", "")
         mma = c["UTCHMMA"] + c["UTCQMMA"]
         print(f"{short[:58]:58s} {c['_n']:6d} | {mma:3d} | {c['UTCBAR']:3d} | {c['LDTM']:3d} | {c['STTM']:3d} | {c['UTMALDG']:3d} | {c['UTMASTG']:3d} | {c['UBLKCP']:3d} | "
               f"{c['LDGSTS']:3d} | {c['SYNCS']:3d} | {c['HMMA']:3d} | {usage.get(mangled, '')}")
