@@ -140,7 +140,10 @@ class GraphSAGEModel(nn.Module):
         else:
             graph = edge_index if isinstance(edge_index, ops.CSRGraph) else ops.get_graph(edge_index, n_nodes)
         if (not torch.is_grad_enabled() and not self.training and self.out_channels == 1 and graph.plan is None
-                and x.dtype in (torch.float32, cd)):
+                and x.dtype in (torch.float32, cd)
+                and (cd == torch.float32 or not torch.cuda.is_current_stream_capturing())):
+            # (under stream capture with bf16 activations the piecewise path stays: it casts the weights INSIDE the graph, so a
+            # replay after a parameter update sees the new values; the cached bf16 copies below would be frozen into the graph)
             # inference: the whole forward behind one C call (dfw_graphsage_forward) - the same launches as below, bit-identical,
             # without ~0.5 ms of Python between them (graphs with a block plan keep the piecewise path: its aggregation differs)
             out = ops.graphsage_forward(graph, x, self._forward_weights(x.dtype, cd), cd, float(self.norms[0].eps) if self.num_layers else 1e-5)

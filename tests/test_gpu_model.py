@@ -530,3 +530,26 @@ def test_one_call_inference_forward_is_bit_identical_to_the_piecewise_path(cd):
         assert torch.equal(fast2, slow2) and not torch.equal(fast2, fast)
     finally:
         ops.graphsage_forward = real
+
+
+@pytest.mark.parametrize("cd", [torch.float32, torch.bfloat16])
+def test_graphed_forward_sees_parameter_updates(cd):
+    """A captured inference graph must not freeze the weights: after an in-place parameter update (an optimizer step between two
+    validation passes) a replay gives the fresh eager forward.  fp32 graphs read the Parameters' own storage; bf16 graphs re-cast
+    the weights inside the graph."""
+    from deep_fem_uav_wing.gnn import synth
+    from deep_fem_uav_wing.gnn.graphed import GraphedForward
+
+    GraphSAGEModel, _, _, _ = _models()
+    m = synth.surface_tri_wing(3000, seed=5)
+    x, ei = torch.from_numpy(m["x"]).cuda(), torch.from_numpy(m["edge_index"]).cuda()
+    torch.manual_seed(1)
+    model = GraphSAGEModel(10, 64, 1, 2, dropout=0.0).cuda().eval().set_compute_dtype(cd)
+    gf = GraphedForward(model)
+    with torch.no_grad():
+        a = gf(x, ei).clone()
+        assert torch.equal(a, model(x, ei))
+        for p_ in model.parameters():
+            p_.mul_(1.05)
+        b = gf(x, ei).clone()
+        assert torch.equal(b, model(x, ei)) and not torch.equal(a, b)
