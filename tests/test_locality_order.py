@@ -29,3 +29,22 @@ def test_locality_order_is_a_permutation_and_compacts_blocks():
     p = torch.rand(1000, 3)
     nid = ops.locality_order(p, torch.zeros(2, 0, dtype=torch.long))
     assert torch.equal(torch.sort(nid).values, torch.arange(1000))
+
+
+def test_static_mesh_is_recognised_from_its_second_use_and_by_identity_only():
+    """Large-mesh preparation policy (``model.mesh_plan = 'auto'``): a mesh counts as static from the SECOND forward on the same
+    edge_index tensor OBJECT; a new tensor - even one the allocator places at the address of a freed one - starts over."""
+    ops._SEEN_MESHES.clear()
+    a = torch.zeros(2, 10, dtype=torch.long)
+    assert not ops.static_mesh_seen_before(a)
+    assert ops.static_mesh_seen_before(a) and ops.static_mesh_seen_before(a)
+    b = a.clone()
+    assert not ops.static_mesh_seen_before(b) and ops.static_mesh_seen_before(b)
+    ident = id(a)
+    del a
+    c = torch.zeros(2, 10, dtype=torch.long)  # may or may not reuse the Python object slot of `a`
+    if id(c) == ident:
+        assert not ops.static_mesh_seen_before(c)  # the weak reference of the dead tensor does not vouch for the new one
+    for _ in range(40):  # bounded
+        ops.static_mesh_seen_before(torch.zeros(2, 1, dtype=torch.long))
+    assert len(ops._SEEN_MESHES) <= 16
