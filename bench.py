@@ -440,6 +440,66 @@ def partitioned_cfg4(device, rank, world, iters=5):
 
 
 # --------------------------------------------------------------------------------------------
+# BASELINE.json config 1: the reference's own CPU-runnable case - ONE 20k-node mesh, H = 64, L = 3, fp32, eval (inference_gnn.py:224-328)
+def cfg1_block(device, with_cpu=True, iters=50):
+    """Latency of one inference forward on a 20k-node mesh (surface-tri and tet lattice): launched from Python through the public
+    API (``model(x, edge_index)``, CSR cached after the first call: eval + no_grad takes ``dfw_graphsage_forward``), replayed from a
+    CUDA graph, and the oracle port on the host cores beside it.  Wall-clock per call incl. the host side (synchronised)."""
+    from deep_fem_uav_wing.gnn import ops
+    from deep_fem_uav_wing.gnn.graphed import GraphedForward
+    from deep_fem_uav_wing.gnn.model import GraphSAGEModel
+
+    synth = _synth()
+    out = {"hidden": 64, "layers": 3, "dtype": "f32", "nodes": 20000, "iters": iters}
+    for kind, gen in (("tri", synth.surface_tri_wing), ("tet", synth.tet_lattice_wing)):
+        m = gen(20000, seed=42)
+        x, ei = torch.from_numpy(m["x"]).to(device), torch.from_numpy(m["edge_index"]).to(device)
+        torch.manual_seed(42)
+        model = GraphSAGEModel(10, 64, 1, 3).to(device).eval()
+
+        def wall(fn):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize(device)
+            ts = []
+            for _ in range(iters):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize(device)
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            return ts[len(ts) // 2] * 1e3
+
+        with torch.no_grad():
+            eager_ms = wall(lambda: model(x, ei))
+            replay, _ = GraphedForward(model).capture_resident(x, ops.get_graph(ei, x.shape[0]))
+            graph_ms = wall(replay)
+        ent = {"N": int(x.shape[0]), "E": int(ei.shape[1]), "eager_ms": round(eager_ms, 4), "cuda_graph_ms": round(graph_ms, 4),
+               "nodes_per_sec_graph": x.shape[0] / (graph_ms * 1e-3)}
+        if with_cpu:
+            from oracle.sage_oracle import GraphSAGEModelRef
+
+            torch.set_num_threads(os.cpu_count() or 1)
+            ref = GraphSAGEModelRef(10, 64, 1, 3, dropout=0.0).eval()
+            ref.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()}, strict=True)
+            xc, ec = x.cpu(), ei.cpu()
+            with torch.no_grad():
+                ref(xc, ec)
+                cs = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    o_ref = ref(xc, ec)
+                    cs.append(time.perf_counter() - t0)
+                got = model(x, ei).cpu()
+            cs.sort()
+            ent["cpu_oracle_ms"] = round(cs[len(cs) // 2] * 1e3, 3)
+            ent["fwd_rel_err_vs_oracle"] = float((got - o_ref).abs().max() / o_ref.abs().max())
+            torch.set_num_threads(1)
+        out[kind] = ent
+        ops.clear_graph_cache()
+    return out
+
+
 # BASELINE.json config 5: design-screening batch inference, case list sharded over the ranks, no communication
 # --------------------------------------------------------------------------------------------
 def cfg5_block(device, rank, world, dist_on, n_cases=10000, nodes=20000, per_launch=16, distinct=48):
@@ -804,9 +864,11 @@ def main():
                "what": "same training step, device-resident, on 4 x 50k-node TET-lattice meshes (degree ~14), 2 batches cycled"}
 
     # ---- config 5 (every N), config 4's aggregation roofline (N = 1), config 4 partitioned over the ranks (N > 1) ---------
-    cfg5 = agg4 = part4 = None
+    cfg5 = agg4 = part4 = cfg1 = None
     if not args.no_extras:
         cfg5 = cfg5_block(device, rank, world, dist_on)
+        if rank == 0 and world == 1:
+            cfg1 = cfg1_block(device, with_cpu=not args.no_cpu_baseline)
         if world == 1:
             agg4 = aggregation_cfg4(device, pk)
         else:
@@ -832,7 +894,7 @@ def main():
             "infer": infer,
             "aggregation": {"kernel": "dfw_sage_aggregate (forward mean, this workload)", "achieved_GBps": kernels.get("aggregate", {}).get("achieved_GBps"),
                             "hbm_frac": kernels.get("aggregate", {}).get("hbm_frac")},
-            "aggregation_cfg4": agg4, "partitioned_cfg4": part4, "cfg5": cfg5, "tet_batch": tet, "parity": gates,
+            "aggregation_cfg4": agg4, "partitioned_cfg4": part4, "cfg1": cfg1, "cfg5": cfg5, "tet_batch": tet, "parity": gates,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         }
         emit(line)
