@@ -494,3 +494,42 @@ def test_node_features_batched_equals_per_case_calls(ops):
     xn, yn = ops.node_features_batched(torch.cat([torch.from_numpy(m["pos"]) for m in meshes]).cuda(), torch.cat([torch.from_numpy(m["normal"]) for m in meshes]).cuda(), None,
                                        torch.tensor(gps, dtype=torch.float32).cuda(), torch.from_numpy(ptr).cuda(), 2000, normalize_pos=False)
     assert yn is None and torch.equal(xn[:, 3:], xb[:, 3:]) and torch.equal(xn[:, :3], torch.cat([torch.from_numpy(m["pos"]) for m in meshes]).cuda())
+
+
+@pytest.mark.parametrize("dt,H,N", [(torch.float32, 128, 128 * 2 + 1), (torch.float32, 128, 128 * 5 + 127), (torch.bfloat16, 64, 128 * 3 + 77),
+                                    (torch.bfloat16, 256, 128 * 2 + 9)])
+def test_tensor_core_linear_writes_nothing_outside_its_rows(ops, dt, H, N):
+    """Guard bands around every output of the fused SAGE linear (ragged last tile: the persistent kernel's epilogue takes its
+    predicated path there): `out`, `pre` and the LayerNorm statistics are written for rows 0..N-1 only, and the guarded call gives
+    the same bits as the plain wrapper.  (compute-sanitizer is not available on the GPU pool: this is the bounds check.)"""
+    from deep_fem_uav_wing.gnn import _cabi
+
+    lib = _cabi.lib
+    G = 160  # guard rows on both sides
+    torch.manual_seed(N)
+    agg = torch.randn(N, H, device="cuda").to(dt)
+    x = torch.randn(N, H, device="cuda").to(dt)
+    wl = (torch.randn(H, H, device="cuda") / H ** 0.5).to(dt)
+    wr = (torch.randn(H, H, device="cuda") / H ** 0.5).to(dt)
+    b, g, be = torch.randn(H, device="cuda"), torch.rand(H, device="cuda") + 0.5, torch.randn(H, device="cuda")
+    ref_out, ref_pre, ref_stats, _ = ops.linear_fwd(agg, wl, x, wr, bias=b, ln=(g, be), relu=True, residual=x, dropout_p=0.1, seed=7, save_pre=True)
+
+    def guarded(cols, dtype, sentinel):
+        buf = torch.full((N + 2 * G, cols), sentinel, dtype=dtype, device="cuda")
+        return buf, buf[G:G + N]
+
+    sent = 1024.0  # exact in bf16
+    out_b, out = guarded(H, dt, sent)
+    pre_b, pre = guarded(H, dt, sent)
+    st_b, st = guarded(2, torch.float32, sent)
+    flags = _cabi.EP_LAYERNORM | _cabi.EP_RELU | _cabi.EP_RESIDUAL | _cabi.EP_DROPOUT
+    dtc = _cabi.DFW_F32 if dt == torch.float32 else _cabi.DFW_BF16
+    ws_bytes = lib.dfw_linear_ws_bytes(H, H, H, dtc)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    _cabi.check(lib.dfw_linear_fwd(agg.data_ptr(), wl.data_ptr(), H, x.data_ptr(), wr.data_ptr(), H, b.data_ptr(), g.data_ptr(), be.data_ptr(), 1e-5,
+                                   x.data_ptr(), 0.1, 7, out.data_ptr(), pre.data_ptr(), st.data_ptr(), None, None, None, N, H, flags, dtc,
+                                   ws.data_ptr(), ws_bytes, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out) and torch.equal(pre, ref_pre) and torch.equal(st, ref_stats)
+    for buf in (out_b, pre_b, st_b):
+        assert bool((buf[:G].float() == sent).all()) and bool((buf[G + N:].float() == sent).all()), "a row outside [0, N) was written"
