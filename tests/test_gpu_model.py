@@ -553,3 +553,38 @@ def test_graphed_forward_sees_parameter_updates(cd):
             p_.mul_(1.05)
         b = gf(x, ei).clone()
         assert torch.equal(b, model(x, ei)) and not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cd", [torch.float32, torch.bfloat16])
+def test_one_call_forward_stays_inside_its_output_and_workspace(cd):
+    """dfw_graphsage_forward through the raw C ABI with guard bands behind `out` and behind the workspace it asked for."""
+    from deep_fem_uav_wing.gnn import _cabi, ops, synth
+
+    GraphSAGEModel, _, _, _ = _models()
+    lib = _cabi.lib
+    m = synth.surface_tri_wing(3000, seed=9)
+    x, ei = torch.from_numpy(m["x"]).cuda(), torch.from_numpy(m["edge_index"]).cuda()
+    n = x.shape[0]
+    torch.manual_seed(2)
+    model = GraphSAGEModel(10, 128, 1, 2, dropout=0.0).cuda().eval().set_compute_dtype(cd)
+    with torch.no_grad():
+        want = model(x, ei)
+    g = ops.get_graph(ei, n)
+    fw = model._forward_weights(x.dtype, cd)
+    dtc = _cabi.DFW_F32 if cd == torch.float32 else _cabi.DFW_BF16
+    ws_bytes = lib.dfw_graphsage_forward_ws_bytes(n, 10, 64, 128, 64, _cabi.DFW_F32, dtc)
+    guard = 1 << 16
+    ws = torch.full((ws_bytes + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    out_b = torch.full((n + 1024,), 777.0, dtype=torch.float32, device="cuda")
+    _cabi.check(lib.dfw_graphsage_forward(g.rowptr.data_ptr(), g.col.data_ptr(), g.inv_deg.data_ptr(), x.data_ptr(), _cabi.DFW_F32, fw.array, 2, n, g.num_edges,
+                                          10, 64, 128, 64, 1e-5, dtc, out_b.data_ptr(), ws.data_ptr(), ws_bytes, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = out_b[:n].unsqueeze(1)
+    if cd != torch.float32:
+        got = got.to(cd).float()  # (the model hands the decoder's fp32 row dot over in the compute dtype)
+    assert torch.equal(got, want.float())
+    assert bool((out_b[n:] == 777.0).all()) and bool((ws[ws_bytes:] == 0xA5).all())
+    # too small a workspace is refused, not overrun
+    rc = lib.dfw_graphsage_forward(g.rowptr.data_ptr(), g.col.data_ptr(), g.inv_deg.data_ptr(), x.data_ptr(), _cabi.DFW_F32, fw.array, 2, n, g.num_edges,
+                                   10, 64, 128, 64, 1e-5, dtc, out_b.data_ptr(), ws.data_ptr(), ws_bytes // 2, torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"workspace" in lib.dfw_last_error()
