@@ -128,7 +128,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
             : "=r"(ok)
             : "r"(addr), "r"(parity), "r"(20000u)
             : "memory");
-        if (!ok && ++spins > (1u << 22)) {
+        if (!ok && ++spins > (1u << 20)) {
             printf("dfw_aggregate_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
             __trap();
         }

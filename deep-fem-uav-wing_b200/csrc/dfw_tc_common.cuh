@@ -37,7 +37,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(addr), "r"(parity), "r"(20000u)
             : "memory");
-        if (!ok && ++spins > (1u << 24)) {  // a legitimate wait lasts microseconds: this is a protocol bug, fail loudly
+        if (!ok && ++spins > (1u << 20)) {  // a legitimate wait lasts microseconds (a failed try_wait sleeps up to 20 us): protocol bug, fail loudly
             printf("dfw_linear_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
             __trap();
         }
