@@ -279,7 +279,11 @@ extern "C" int dfw_graphsage_forward(const int32_t* rowptr, const int32_t* col, 
     void* mid = b + w.o_mid;
     // encoder (model.py:52-57): the first linear reads the raw features in THEIR dtype (see gnn/model.py), its output enters the compute dtype
     int rc;
-    if (mixed) {
+    if (mixed && in_dim <= 16 && enc_mid % 4 == 0 && dtype == DFW_BF16) {
+        // fp32 features, fp32 weights, fp32 arithmetic, bf16 result in one launch (same bits as the fp32 launch + dfw_cast below)
+        rc = dfw_linear_fwd(x, weights[0], in_dim, nullptr, nullptr, 0, (const float*)weights[1], nullptr, nullptr, 1e-5f, nullptr, 0.f, 0, mid, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, N, enc_mid, DFW_EP_RELU | DFW_EP_OUT_BF16, DFW_F32, lin, w.lin_bytes, stream);
+    } else if (mixed) {
         void* mid32 = b + w.o_mid32;
         rc = dfw_linear_fwd(x, weights[0], in_dim, nullptr, nullptr, 0, (const float*)weights[1], nullptr, nullptr, 1e-5f, nullptr, 0.f, 0, mid32, nullptr,
                             nullptr, nullptr, nullptr, nullptr, N, enc_mid, DFW_EP_RELU, DFW_F32, lin, w.lin_bytes, stream);

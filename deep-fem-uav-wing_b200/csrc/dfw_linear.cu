@@ -613,9 +613,9 @@ struct SmallKStage {
     }
 };
 
-template <typename T, int KP>
+template <typename T, int KP, typename TO = T>
 __global__ void __launch_bounds__(256, 3) k_smallk_fwd_tiled(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
-                                                              T* __restrict__ out, int64_t N, int K, int Hout, int relu) {
+                                                              TO* __restrict__ out, int64_t N, int K, int Hout, int relu) {
     __shared__ __align__(16) float xs[2][kSmallTile * KP];
     const int fq = Hout / 4;      // threads per row (<= 256)
     const int rpi = 256 / fq;     // rows per pass
@@ -789,7 +789,7 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
     if (N == 0) return 0;
     if ((flags & DFW_EP_DROPOUT) && dropout_p == 0.f) flags &= ~DFW_EP_DROPOUT;
     DFW_REQUIRE(!(flags & DFW_EP_LAYERNORM) || (ln_gamma && ln_beta), "dfw_linear_fwd: DFW_EP_LAYERNORM needs gamma and beta");
-    if (ws && !force_simt() && linear_tc_eligible(N, Hout, k1, a2 ? k2 : 0, dtype, a1, a2) &&
+    if (!(flags & DFW_EP_OUT_BF16) && ws && !force_simt() && linear_tc_eligible(N, Hout, k1, a2 ? k2 : 0, dtype, a1, a2) &&
         ws_bytes >= linear_tc_ws_bytes(Hout, k1, a2 ? k2 : 0, dtype) && aligned16(out ? out : a1) &&
         (!pre_out || aligned16(pre_out)) && (!residual || aligned16(residual))) {
         tc::Args t{};
@@ -804,6 +804,11 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
     }
     DFW_REQUIRE(!(flags & DFW_EP_TRANSPOSE_W), "dfw_linear_fwd: DFW_EP_TRANSPOSE_W needs a tensor-core eligible shape "
                 "(ask dfw_linear_tc_eligible first)");
+    const bool out_bf16 = flags & DFW_EP_OUT_BF16;
+    flags &= ~DFW_EP_OUT_BF16;
+    DFW_REQUIRE(!out_bf16 || (dtype == DFW_F32 && !a2 && k1 <= kSmallKMax && Hout % 4 == 0 && out && !pre_out && !rowdot_out &&
+                              !(flags & ~DFW_EP_RELU) && aligned16(out) && !force_simt()),
+                "dfw_linear_fwd: DFW_EP_OUT_BF16 is the tiny-K fp32 linear only (single operand, k1 <= %d, Hout %% 4 == 0, ReLU at most)", kSmallKMax);
     if (!force_simt() && !a2 && k1 <= kSmallKMax && Hout % 4 == 0 && Hout <= 1024 && out && !pre_out && !rowdot_out &&
         !(flags & ~DFW_EP_RELU) && aligned16(out)) {
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -817,7 +822,13 @@ extern "C" int dfw_linear_fwd(const void* a1, const void* w1, int64_t k1, const 
     if (k1 <= 4) DFW_SK_FWD(TT, 4); else if (k1 <= 8) DFW_SK_FWD(TT, 8); else if (k1 <= 12) DFW_SK_FWD(TT, 12);       \
     else DFW_SK_FWD(TT, 16);                                                                                         \
     } while (0)
-        if (dtype == DFW_F32) DFW_SK_FWD_K(float); else DFW_SK_FWD_K(__nv_bfloat16);
+        if (out_bf16) {
+#define DFW_SK_FWD_MIX(KPV) \
+    k_smallk_fwd_tiled<float, KPV, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)a1, (const float*)w1, bias, (__nv_bfloat16*)out, N, (int)k1, \
+                                                                           (int)Hout, flags & DFW_EP_RELU)
+            if (k1 <= 4) DFW_SK_FWD_MIX(4); else if (k1 <= 8) DFW_SK_FWD_MIX(8); else if (k1 <= 12) DFW_SK_FWD_MIX(12); else DFW_SK_FWD_MIX(16);
+#undef DFW_SK_FWD_MIX
+        } else if (dtype == DFW_F32) DFW_SK_FWD_K(float); else DFW_SK_FWD_K(__nv_bfloat16);
 #undef DFW_SK_FWD_K
 #undef DFW_SK_FWD
         DFW_LAUNCH_CHECK();

@@ -13,7 +13,7 @@ _PKG_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 LIB_PATH = os.environ.get("DFW_B200_LIB", os.path.join(_PKG_ROOT, "lib", "libdfw_b200.so"))
 
 DFW_F32, DFW_BF16 = 0, 1
-EP_RELU, EP_LAYERNORM, EP_RESIDUAL, EP_DROPOUT, EP_SEED_IS_PTR, EP_TRANSPOSE_W = 1, 2, 4, 8, 16, 32
+EP_RELU, EP_LAYERNORM, EP_RESIDUAL, EP_DROPOUT, EP_SEED_IS_PTR, EP_TRANSPOSE_W, EP_OUT_BF16 = 1, 2, 4, 8, 16, 32, 64
 
 # name -> (restype, argtypes); must list every symbol of include/dfw_b200.h
 SIGNATURES = {

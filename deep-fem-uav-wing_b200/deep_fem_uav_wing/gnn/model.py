@@ -162,9 +162,15 @@ class GraphSAGEModel(nn.Module):
         # The first linear reads the 10 raw features in THEIR dtype: normalised positions rounded to bf16 (8 bits) move a
         # trained model's output by percents where the stress field is steep (wing tip), while the layer is 10-wide and
         # costs nothing in fp32; its 64-wide output is what enters the compute dtype.
-        h = x if (x.dtype == torch.float32 and cd == torch.bfloat16) else ops.cast_ad(x, cd)
-        h = ops.LinearFn.apply(h, enc0.weight, enc0.bias, True, 0.0, 0)
-        h = ops.cast_ad(h, cd)
+        if (x.dtype == torch.float32 and cd == torch.bfloat16 and not torch.is_grad_enabled() and self.in_channels <= 16
+                and enc0.out_features % 4 == 0):
+            # inference: fp32 arithmetic, bf16 result in one launch (the bits dfw_cast would give, without the fp32 [N, 64] round trip)
+            h, _, _, _ = ops.linear_fwd(x.contiguous(), ops._f32(enc0.weight.detach()), bias=ops._f32(enc0.bias.detach()) if enc0.bias is not None else None,
+                                        relu=True, out_bf16=True)
+        else:
+            h = x if (x.dtype == torch.float32 and cd == torch.bfloat16) else ops.cast_ad(x, cd)
+            h = ops.LinearFn.apply(h, enc0.weight, enc0.bias, True, 0.0, 0)
+            h = ops.cast_ad(h, cd)
         h = ops.LinearFn.apply(h, enc2.weight, enc2.bias, True, 0.0, 0)
 
         for i, (conv, norm) in enumerate(zip(self.convs, self.norms)):

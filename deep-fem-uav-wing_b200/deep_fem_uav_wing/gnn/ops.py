@@ -624,9 +624,10 @@ def cfg4_aggregation_paths(edge_index, num_nodes, pos, x):
 
 
 def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=False, residual=None, dropout_p=0.0, seed=0,
-               save_pre=False, rowdot=None, want_out=True, transpose_w=False, label="linear_fwd"):
+               save_pre=False, rowdot=None, want_out=True, transpose_w=False, label="linear_fwd", out_bf16=False):
     """See ``dfw_linear_fwd``.  ``ln`` = (gamma, beta); ``rowdot`` = (w fp32 [Hout], b fp32 [1] or None).
-    ``transpose_w``: ``w1``/``w2`` are ``[k, Hout]`` (a forward layer's weights used by its input gradient)."""
+    ``transpose_w``: ``w1``/``w2`` are ``[k, Hout]`` (a forward layer's weights used by its input gradient).
+    ``out_bf16``: fp32 tiny-K linear whose result is stored as bf16 (``DFW_EP_OUT_BF16``: the encoder's first layer in bf16 mode)."""
     _require_cuda(a1, "input")
     N, k1 = a1.shape
     dev, dt = a1.device, a1.dtype
@@ -651,7 +652,9 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, ln=None, eps=1e-5, relu=Fals
     seed_v, seed_flag = _seed_arg(seed)
     if dropout_p > 0.0:
         flags |= EP_DROPOUT | seed_flag
-    out = torch.empty(N, Hout, dtype=dt, device=dev) if want_out else None
+    if out_bf16:
+        flags |= _cabi.EP_OUT_BF16
+    out = torch.empty(N, Hout, dtype=torch.bfloat16 if out_bf16 else dt, device=dev) if want_out else None
     pre = torch.empty(N, Hout, dtype=dt, device=dev) if save_pre else None
     stats = torch.empty(N, 2, dtype=torch.float32, device=dev) if (save_pre and ln is not None) else None
     rd_out = torch.empty(N, dtype=torch.float32, device=dev) if rowdot is not None else None

@@ -42,9 +42,12 @@ enum {
     DFW_EP_DROPOUT = 8,   /* inverted dropout (train only)                      model.py:93, :70        */
     DFW_EP_SEED_IS_PTR = 16, /* `seed` is a DEVICE pointer to one uint64 (read by the kernel): lets a captured CUDA graph
                              draw a fresh dropout mask on every replay */
-    DFW_EP_TRANSPOSE_W = 32 /* dfw_linear_fwd only: w1/w2 are given as [k, Hout] row-major (the FORWARD layer's weights,
+    DFW_EP_TRANSPOSE_W = 32, /* dfw_linear_fwd only: w1/w2 are given as [k, Hout] row-major (the FORWARD layer's weights,
                              used by its input gradient g W instead of x W^T); the transposition rides in the weight
                              preparation launch.  Needs a tensor-core eligible shape: ask dfw_linear_tc_eligible */
+    DFW_EP_OUT_BF16 = 64  /* dfw_linear_fwd with dtype = DFW_F32, single operand, k1 <= 16, no LayerNorm / dropout / residual
+                             (the encoder's first linear, model.py:53): `out` is written as bf16 - the fp32 result rounded to
+                             nearest even at the store, i.e. what dfw_cast would make of it, without the fp32 round trip */
 };
 
 const char* dfw_last_error(void);

@@ -533,3 +533,22 @@ def test_tensor_core_linear_writes_nothing_outside_its_rows(ops, dt, H, N):
     assert torch.equal(out, ref_out) and torch.equal(pre, ref_pre) and torch.equal(st, ref_stats)
     for buf in (out_b, pre_b, st_b):
         assert bool((buf[:G].float() == sent).all()) and bool((buf[G + N:].float() == sent).all()), "a row outside [0, N) was written"
+
+
+def test_tiny_k_linear_with_bf16_output_equals_fp32_launch_plus_cast(ops):
+    """DFW_EP_OUT_BF16: the encoder's first linear (fp32 features and weights) stored as bf16 in one launch gives the bits of the
+    fp32 launch followed by dfw_cast; shapes the tiny-K kernel does not take are refused."""
+    from deep_fem_uav_wing.gnn import _cabi
+
+    torch.manual_seed(0)
+    for n, k, h in ((5000, 10, 64), (777, 3, 128), (1, 16, 4)):
+        x = torch.randn(n, k, device="cuda")
+        w = torch.randn(h, k, device="cuda") / k ** 0.5
+        b = torch.randn(h, device="cuda")
+        ref, _, _, _ = ops.linear_fwd(x, w, bias=b, relu=True)
+        got, _, _, _ = ops.linear_fwd(x, w, bias=b, relu=True, out_bf16=True)
+        assert got.dtype == torch.bfloat16 and torch.equal(got, ops.cast(ref, torch.bfloat16))
+    x = torch.randn(256, 64, device="cuda")
+    w = torch.randn(128, 64, device="cuda")
+    with pytest.raises(RuntimeError, match="DFW_EP_OUT_BF16"):
+        ops.linear_fwd(x, w, relu=True, out_bf16=True)  # K = 64 is a tensor-core shape
