@@ -429,16 +429,22 @@ def build_agg_plan(rowptr: torch.Tensor, col: torch.Tensor, num_nodes: int) -> A
     return AggPlan(N, blk_meta, plan_src, plan_rec, plan_slot, status)
 
 
-def aggregate_tc(plan: AggPlan, row_scale, x, num_edges: int = 0):
-    """``dfw_sage_aggregate_tc``: mean (``row_scale = inv_deg``) or sum (None) of neighbour rows, bf16, H in {64, 128, 256}."""
+def aggregate_tc(plan: AggPlan, row_scale, x, num_edges: int = 0, n_rows: int | None = None):
+    """``dfw_sage_aggregate_tc``: mean (``row_scale = inv_deg``) or sum (None) of neighbour rows, bf16, H in {64, 128, 256}.
+    ``n_rows``: the plan describes ``n_rows`` destination rows whose sources index a LONGER tensor ``x`` (own rows followed by
+    halo rows, ``gnn/partition.py``): a block's own rows are the first ``n_rows`` rows of ``x``, every other source is a halo row."""
     _require_cuda(x, "x")
     if x.dtype != torch.bfloat16:
         raise TypeError(f"aggregate_tc takes bfloat16 rows, got {x.dtype}")
     x = x.contiguous()
     N, H = x.shape
+    if n_rows is not None:
+        if n_rows > N:
+            raise ValueError(f"n_rows = {n_rows} exceeds the {N} rows of x")
+        N = int(n_rows)
     if N != plan.num_nodes:
         raise ValueError(f"plan was built for {plan.num_nodes} rows, x has {N}")
-    out = torch.empty_like(x)
+    out = torch.empty(N, H, dtype=x.dtype, device=x.device)
     amin = 2 * N * H * 2 + 4 * num_edges + 4 * (N + 1)
     with torch.cuda.device(x.device), _prof("aggregate_tc", amin):
         check(lib.dfw_sage_aggregate_tc(plan.blk_meta.data_ptr(), plan.plan_src.data_ptr(), plan.plan_rec.data_ptr(), plan.plan_slot.data_ptr(),

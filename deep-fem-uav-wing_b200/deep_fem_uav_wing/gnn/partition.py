@@ -11,8 +11,8 @@ GPU: a 1-D partition of the nodes with a halo exchange per SAGE layer.
   ``all_to_all_single`` over NCCL/NVLink - the path's only exchange step), appends the received rows behind
   its own, aggregates over its LOCAL CSR (destinations = own rows, sources = own + halo rows) and runs the
   fused linear on its own rows.  Encoder, decoder and the epilogue are row-local.
-* The arithmetic is the single-GPU path's: the same ``dfw_sage_aggregate`` / ``dfw_linear_fwd`` launches on the
-  same rows; a row's remote neighbours are numbered behind its local ones, so its fp32 neighbour sum is taken in a
+* The arithmetic is the single-GPU path's: the same ``dfw_sage_aggregate`` (or, for bf16 rows on pieces of >= 131k rows,
+  ``dfw_sage_aggregate_tc`` with a plan of the local graph) / ``dfw_linear_fwd`` launches on the same rows; a row's remote neighbours are numbered behind its local ones, so its fp32 neighbour sum is taken in a
   different order - the result equals the unpartitioned forward up to fp32 rounding
   (``tests/test_partition_nccl.py``: 2 ranks vs 1 GPU, 1e-5).
 
@@ -125,16 +125,28 @@ class PartitionedMeshInference:
         rowptr, col, _, inv_deg, _ = ops.csr_build_raw(self.part.local_edge_index, max(n_ext, 1), want_perm=False)
         self.rowptr, self.col, self.inv_deg = rowptr[: self.part.n_own + 1].contiguous(), col, inv_deg[: self.part.n_own].contiguous()
         self.halo_rows = int(self.part.halo_ids.numel())
+        # bf16 rows on a large enough piece: the tensor-core block aggregation on the LOCAL graph (destinations = own rows, which are
+        # also the first rows of [own | halo], so a block's own rows are plain tiles and every remote source is one more halo row)
+        self.plan = None
+        n_own, e_loc = self.part.n_own, int(self.col.numel())
+        if (model.compute_dtype == torch.bfloat16 and model.hidden_channels in ops.TC_AGG_WIDTHS and n_own >= ops.TC_AGG_MIN_NODES
+                and e_loc > 0):
+            plan = ops.build_agg_plan(self.rowptr, self.col, n_own)
+            if plan.check() and e_loc / max(n_own, 1) >= ops.TC_AGG_MIN_REUSE * plan.staged_rows_per_row:
+                self.plan = plan
 
     @torch.no_grad()
     def forward(self) -> torch.Tensor:
         m = self.model
         cd = m.compute_dtype
         x = self.x_own
-        h = x if (x.dtype == torch.float32 and cd == torch.bfloat16) else ops.cast(x, cd)
         enc0, enc2 = m.encoder[0], m.encoder[2]
-        h, _, _, _ = ops.linear_fwd(h, ops._w(enc0.weight, h.dtype), bias=ops._f32(enc0.bias.detach()), relu=True)
-        h = ops.cast(h, cd)
+        if x.dtype == torch.float32 and cd == torch.bfloat16 and m.in_channels <= 16 and enc0.out_features % 4 == 0:
+            h, _, _, _ = ops.linear_fwd(x, ops._f32(enc0.weight.detach()), bias=ops._f32(enc0.bias.detach()), relu=True, out_bf16=True)  # as model.py
+        else:
+            h = x if (x.dtype == torch.float32 and cd == torch.bfloat16) else ops.cast(x, cd)
+            h, _, _, _ = ops.linear_fwd(h, ops._w(enc0.weight, h.dtype), bias=ops._f32(enc0.bias.detach()), relu=True)
+            h = ops.cast(h, cd)
         h, _, _, _ = ops.linear_fwd(h, ops._w(enc2.weight, cd), bias=ops._f32(enc2.bias.detach()), relu=True)
         H = h.shape[1]
         for conv, norm in zip(m.convs, m.norms):
@@ -142,7 +154,10 @@ class PartitionedMeshInference:
             halo = torch.empty(self.halo_rows, H, dtype=h.dtype, device=h.device)
             dist.all_to_all_single(halo, send, output_split_sizes=self.part.recv_counts, input_split_sizes=self.part.send_counts, group=self.pg)
             h_ext = torch.cat([h, halo], dim=0)
-            agg = ops.aggregate_rows(self.rowptr, self.col, self.inv_deg, h_ext, self.part.n_own)
+            if self.plan is not None:
+                agg = ops.aggregate_tc(self.plan, self.inv_deg, h_ext, int(self.col.numel()), n_rows=self.part.n_own)
+            else:
+                agg = ops.aggregate_rows(self.rowptr, self.col, self.inv_deg, h_ext, self.part.n_own)
             h, _, _, _ = ops.linear_fwd(agg, ops._w(conv.lin_l.weight, cd), h, ops._w(conv.lin_r.weight, cd), bias=ops._f32(conv.lin_l.bias.detach()),
                                         ln=(ops._f32(norm.weight.detach()), ops._f32(norm.bias.detach())), eps=float(norm.eps), relu=True, residual=h)
         dec0, dec3 = m.decoder[0], m.decoder[3]

@@ -147,6 +147,8 @@ int dfw_sage_aggregate_scaled(const int32_t* rowptr, const int32_t* col, const f
  *       it is <= dfw_agg_plan_max_block_edges() (an edge repeated more than 8 times also pushes it above); [1] = total number of staged rows (sum of S over the blocks: the locality
  *       measure, staged rows per output row = [1] / N).  No host synchronisation.
  *     dfw_sage_aggregate_tc: x, out bf16 [N,H], H in {64,128,256}; row_scale fp32 [N] (inv_deg: mean) or NULL (sum).
+ *       Rectangular use (partitioned meshes): `col` may name sources >= N - x then has more than N rows (the N destination rows first,
+ *       halo rows behind them); every source outside a block's own 128 rows is staged as a halo row, wherever it lives.
  * ---------------------------------------------------------------------------------------- */
 int dfw_agg_plan_sizes(int64_t N, int64_t E, int64_t* nblocks, int64_t* src_cap, int64_t* slot_cap);
 int dfw_agg_plan_max_block_edges(void);

@@ -24,14 +24,22 @@ def main():
     from deep_fem_uav_wing.gnn.partition import PartitionedMeshInference
 
     res = {"world": world, "cases": []}
-    for kind, n, h, layers, dtype in (("tet-random", 60000, 64, 3, torch.float32), ("tri", 50000, 128, 4, torch.float32),
-                                      ("tet-random", 120000, 128, 3, torch.bfloat16)):
+    from deep_fem_uav_wing.gnn import ops
+
+    min_nodes, min_reuse = ops.TC_AGG_MIN_NODES, ops.TC_AGG_MIN_REUSE
+    for kind, n, h, layers, dtype, blocks in (("tet-random", 60000, 64, 3, torch.float32, False), ("tri", 50000, 128, 4, torch.float32, False),
+                                              ("tet-random", 120000, 128, 3, torch.bfloat16, False), ("tet-random", 120000, 128, 3, torch.bfloat16, True)):
+        # blocks: the local aggregation runs the tensor-core block kernel on the rectangular [own | halo] layout (the size policy
+        # would leave a 60k-row piece to the gather kernel)
+        ops.TC_AGG_MIN_NODES, ops.TC_AGG_MIN_REUSE = (1000, 0.0) if blocks else (min_nodes, min_reuse)
         mesh = synth.tet_lattice_wing(n, seed=5, node_order="random") if kind.startswith("tet") else synth.surface_tri_wing(n, seed=5)
         x, ei = torch.from_numpy(mesh["x"]).to(device), torch.from_numpy(mesh["edge_index"]).to(device)
         torch.manual_seed(11)  # identical weights on every rank
         model = GraphSAGEModel(10, h, 1, layers, dropout=0.0).to(device).eval().set_compute_dtype(dtype)
         model.node_reorder = "never"
         pm = PartitionedMeshInference(model, x, ei)
+        assert (pm.plan is not None) == blocks, "local block plan expected exactly in the `blocks` case"
+        ops.TC_AGG_MIN_NODES, ops.TC_AGG_MIN_REUSE = min_nodes, min_reuse
         out_own = pm()
         full = pm.gather(out_own)
         torch.cuda.synchronize()
@@ -43,7 +51,7 @@ def main():
                 ref = model(x, ei)
             err = ((full.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
             res["cases"].append({"mesh": kind, "N": int(x.shape[0]), "hidden": h, "layers": layers, "dtype": str(dtype).replace("torch.", ""),
-                                 "rel_max_vs_unpartitioned": err, "halo_rows_per_rank": [int(t[0]) for t in allh], "own_rows_per_rank": [int(t[1]) for t in allh]})
+                                 "local_aggregation": "tensor-core blocks" if blocks else "gather", "rel_max_vs_unpartitioned": err, "halo_rows_per_rank": [int(t[0]) for t in allh], "own_rows_per_rank": [int(t[1]) for t in allh]})
         dist.barrier()
     if rank == 0:
         with open(out_path, "w") as f:

@@ -29,7 +29,7 @@ def test_partitioned_forward_equals_unpartitioned(tmp_path):
     if os.path.isdir(log_dir):
         with open(os.path.join(log_dir, f"partition_nccl_n{world}.json"), "w") as f:
             json.dump(res, f, indent=1)
-    assert len(res["cases"]) == 3
+    assert len(res["cases"]) == 4 and res["cases"][3]["local_aggregation"] == "tensor-core blocks"
     for c in res["cases"]:
         tol = 1e-5 if c["dtype"] == "float32" else 2e-2
         assert c["rel_max_vs_unpartitioned"] < tol, c
